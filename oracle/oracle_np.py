@@ -1,0 +1,219 @@
+"""Independent numpy twin of the C oracle.  TEST INFRASTRUCTURE ONLY (see oracle/clc_oracle.h).
+
+Written separately from clc_oracle.c, with numpy's LAPACK (lstsq / svd / solve) in place of the hand-written
+dense kernels, so that a transcription error in one restatement shows up as a disagreement between the two.
+Same citations: /root/reference/src/LaseCamCalCeres.cpp, src/pose_local_parameterization.cpp and the published
+Ceres (<= 2.1) trust-region semantics.  PARITY UNPINNED (no reference tests exist; Ceres/Eigen absent here).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+# --- Eigen restatements --------------------------------------------------------------------------------
+def quat_to_rot(q):
+    """Eigen QuaternionBase::toRotationMatrix; q = (x,y,z,w), not normalised."""
+    x, y, z, w = q
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)],
+    ])
+
+
+def quat_mul(a, b):
+    """Eigen quaternion product, (x,y,z,w) order."""
+    ax, ay, az, aw = a
+    bx, by, bz, bw = b
+    return np.array([
+        aw * bx + ax * bw + ay * bz - az * by,
+        aw * by + ay * bw + az * bx - ax * bz,
+        aw * bz + az * bw + ax * by - ay * bx,
+        aw * bw - ax * bx - ay * by - az * bz,
+    ])
+
+
+def pose_plus(x, d):
+    """pose_local_parameterization.cpp:15-32."""
+    q = quat_mul(x[3:7], np.array([d[3] / 2, d[4] / 2, d[5] / 2, 1.0]))
+    return np.concatenate([x[:3] + d[:3], q / np.linalg.norm(q)])
+
+
+def skew(p):
+    """LaseCamCalCeres.cpp:35-42."""
+    return np.array([[0, -p[2], p[1]], [p[2], 0, -p[0]], [-p[1], p[0], 0]])
+
+
+# --- planes ----------------------------------------------------------------------------------------------
+def frame_plane(fp):
+    """LaseCamCalCeres.cpp:227-231, literally: (Tctag^-1)^T (0,0,1,0)."""
+    T = np.eye(4)
+    T[:3, :3] = quat_to_rot(fp[:4])
+    T[:3, 3] = fp[4:7]
+    return np.linalg.inv(T).T @ np.array([0.0, 0.0, 1.0, 0.0])
+
+
+def pi_from_ppp(x1, x2, x3):
+    """utilities.cpp:267-272."""
+    return np.concatenate([np.cross(x1 - x3, x2 - x3), [-x3 @ np.cross(x1, x2)]])
+
+
+def edge_planes(fp):
+    """LaseCamCalCeres.cpp:262-276."""
+    orig = np.array([0.0265 + 0.0165, 0.0265 + 0.0165, 0.0])
+    R, t = quat_to_rot(fp[:4]), fp[4:7]
+    p1c, p2c, p3c = (R @ (np.array(p) - orig) + t for p in ([0, 0, 0], [0.5, 0, 0], [0, 0.5, 0]))
+    z = np.zeros(3)
+    return pi_from_ppp(p1c, p2c, z), pi_from_ppp(p1c, p3c, z)
+
+
+# --- residual table ---------------------------------------------------------------------------------------
+def residual_table(frame_pose, offsets, points, edge_points=None):
+    """Per-residual (plane[4], point[3], scale) in the reference's AddResidualBlock order (:222-295)."""
+    planes, pts, scales = [], [], []
+    for f in range(len(frame_pose)):
+        b, e = int(offsets[f]), int(offsets[f + 1])
+        if e <= b:
+            continue
+        pl = frame_plane(frame_pose[f])
+        s = 1.0 / np.sqrt(float(e - b))
+        for j in range(b, e):
+            planes.append(pl); pts.append(points[j]); scales.append(s)
+        if edge_points is not None:
+            pi1, pi2 = edge_planes(frame_pose[f])
+            planes.append(pi1); pts.append(edge_points[f, 0:3]); scales.append(s)
+            planes.append(pi2); pts.append(edge_points[f, 3:6]); scales.append(s)
+    return np.array(planes).reshape(-1, 4), np.array(pts).reshape(-1, 3), np.array(scales)
+
+
+def evaluate(table, pose7, use_loss=True, cauchy_a=0.05):
+    """PointInPlaneFactor::Evaluate (:43-66) for every row + Ceres CauchyLoss / Corrector / local Jacobian.
+
+    Returns cost, corrected residuals [R], corrected local Jacobian [R,6]."""
+    planes, pts, s = table
+    R = quat_to_rot(pose7[3:7])
+    t = pose7[:3]
+    n = planes[:, :3]
+    pc = pts @ R.T + t
+    r = s * (np.einsum("ij,ij->i", n, pc) + planes[:, 3])
+    J = np.empty((len(r), 6))
+    J[:, :3] = s[:, None] * n
+    # n^T (-R skew(p)) = (p x R^T n)^T
+    m = n @ R
+    J[:, 3:] = s[:, None] * np.cross(pts, m)
+    if not use_loss:
+        return 0.5 * float(r @ r), r, J
+    b = (cauchy_a * s) ** 2
+    c = 1.0 / b
+    summ = 1.0 + (r * r) * c
+    inv = 1.0 / summ
+    rho0 = b * np.log(summ)
+    rho1 = np.maximum(np.finfo(float).tiny, inv)
+    sq = np.sqrt(rho1)
+    return 0.5 * float(np.sum(rho0)), r * sq, J * sq[:, None]
+
+
+def gradient_max_norm(x, g):
+    return float(np.max(np.abs(x - pose_plus(x, -g))))
+
+
+def solve(table, pose7, use_loss=True, cauchy_a=0.05, max_num_iterations=100, verbose=False):
+    """Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy + DENSE_QR with the Ceres defaults
+    (see SURVEY.md section 8(c) / oracle/clc_oracle.c for the line-by-line restatement)."""
+    ftol, gtol, ptol = 1e-6, 1e-10, 1e-8
+    radius, dec = 1e4, 2.0
+    x = np.array(pose7, dtype=float)
+    x_norm = np.linalg.norm(x)
+    cost, r, J = evaluate(table, x, use_loss, cauchy_a)
+    g = J.T @ r
+    scale = 1.0 / (1.0 + np.sqrt(np.sum(J * J, axis=0)))
+    J = J * scale
+    trace = [dict(iteration=0, cost=cost, ok=True, gmax=gradient_max_norm(x, g), radius=radius)]
+    reuse, invalid, diag = False, 0, None
+    term = None
+    while True:
+        last = trace[-1]
+        if last["iteration"] >= max_num_iterations:
+            term = "NO_CONVERGENCE"; break
+        if last["ok"] and last["gmax"] <= gtol:
+            term = "CONVERGENCE_GRADIENT"; break
+        if radius <= 1e-32:
+            term = "CONVERGENCE_MIN_RADIUS"; break
+        it = last["iteration"] + 1
+        if not reuse:
+            diag = np.clip(np.sum(J * J, axis=0), 1e-6, 1e32)
+        D = np.sqrt(diag / radius)
+        A = np.vstack([J, np.diag(D)])
+        rhs = np.concatenate([r, np.zeros(6)])
+        y = np.linalg.lstsq(A, rhs, rcond=None)[0]
+        step = -y
+        reuse = True
+        mr = J @ step
+        model_change = -float(mr @ (r + mr / 2.0))
+        if not (np.all(np.isfinite(step)) and model_change > 0.0):
+            invalid += 1
+            if invalid >= 5:
+                term = "FAILURE"; break
+            radius /= dec; dec *= 2.0
+            trace.append(dict(iteration=it, cost=cost, ok=False, gmax=last["gmax"], radius=radius))
+            continue
+        invalid = 0
+        cand = pose_plus(x, step * scale)
+        cand_cost, _, _ = evaluate(table, cand, use_loss, cauchy_a)
+        step_norm = np.linalg.norm(x - cand)
+        if step_norm <= ptol * (x_norm + ptol):
+            term = "CONVERGENCE_PARAMETER"; break
+        change = cost - cand_cost
+        if abs(change) <= ftol * cost:
+            term = "CONVERGENCE_FUNCTION"; break
+        rho = change / model_change
+        if rho > 1e-3:
+            x = cand
+            x_norm = np.linalg.norm(x)
+            cost, r, J = evaluate(table, x, use_loss, cauchy_a)
+            g = J.T @ r
+            J = J * scale
+            radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3))
+            dec, reuse = 2.0, False
+            trace.append(dict(iteration=it, cost=cost, ok=True, gmax=gradient_max_norm(x, g), radius=radius,
+                              rho=rho, step_norm=step_norm))
+        else:
+            radius /= dec; dec *= 2.0
+            trace.append(dict(iteration=it, cost=cand_cost, ok=False, gmax=0.0, radius=radius, rho=rho,
+                              step_norm=step_norm))
+        if verbose:
+            print(trace[-1])
+    return x, term, trace
+
+
+def information(frame_pose, offsets, points, pose7):
+    """Analysis tail (:318-381): no loss, no edge residuals."""
+    table = residual_table(frame_pose, offsets, points, None)
+    _, r, J = evaluate(table, pose7, use_loss=False)
+    H = J.T @ J
+    return H, -J.T @ r, float(r @ r), np.linalg.svd(H, compute_uv=False)
+
+
+def closed_form(frame_pose, offsets, points):
+    """CamLaserCalClosedSolution (:112-203), literally with a dense A."""
+    rows, rhs = [], []
+    for f in range(len(frame_pose)):
+        pl = frame_plane(frame_pose[f])
+        for j in range(int(offsets[f]), int(offsets[f + 1])):
+            bar = np.array([points[j, 0], points[j, 1], 1.0])
+            rows.append(np.concatenate([pl[:3] * bar[0], pl[:3] * bar[1], pl[:3] * bar[2]]))
+            rhs.append(-pl[3])
+    A, b = np.array(rows), np.array(rhs)
+    AtA = A.T @ A
+    sv = np.linalg.svd(AtA, compute_uv=False)
+    unobservable = bool(np.any(sv < 1e-10))
+    H = np.linalg.solve(AtA, A.T @ b)
+    h1, h2, h3 = H[0:3], H[3:6], H[6:9]
+    Rcl = np.column_stack([h1, h2, np.cross(h1, h2)])
+    Rlc = Rcl.T
+    tlc = -Rlc @ h3
+    U, _, Vt = np.linalg.svd(Rlc)
+    T = np.eye(4)
+    T[:3, :3] = U @ Vt
+    T[:3, 3] = tlc
+    return T, unobservable, AtA, A.T @ b
