@@ -1,0 +1,843 @@
+// clc_api.cu -- host side of libclc_b200.so: the C ABI declared in include/clc_b200.h.
+//
+// No CPU fallback lives here: every entry point drives the sm_100a kernels of clc_kernels.cuh and fails loudly
+// (status code + clc_last_error()) when CUDA is unusable.  The only host arithmetic is O(1) dense work on the
+// reduced 6x6 / 9x9 systems for the two diagnostic outputs the reference prints (singular values, closed form).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only; the library is dlopen()ed so that single-GPU use has no NCCL dependency
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/clc_b200.h"
+#include "clc_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CLC_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(CLC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                                    std::to_string(__LINE__) + ")");                                     \
+  } while (0)
+
+#define CLC_LAUNCH_CHECK()                  \
+  do {                                      \
+    g_launches.fetch_add(1);                \
+    CLC_CUDA(cudaGetLastError());           \
+  } while (0)
+
+// ---- NCCL through dlopen -------------------------------------------------------------------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return &api;
+  tried = true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) {
+    api.error = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+    return &api;
+  }
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(api.handle, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(api.handle, "ncclCommInitRank"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(api.handle, "ncclAllReduce"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(api.handle, "ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(api.handle, "ncclGetErrorString"));
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString) {
+    api.error = "libnccl.so.2 lacks a required symbol";
+    api.handle = nullptr;
+  }
+  return &api;
+}
+
+#define CLC_NCCL(expr)                                                                                   \
+  do {                                                                                                   \
+    ncclResult_t _r = (expr);                                                                            \
+    if (_r != ncclSuccess)                                                                               \
+      return fail(CLC_ERR_NCCL, std::string(#expr) + ": " + nccl_api()->GetErrorString(_r));            \
+  } while (0)
+
+// ---- O(1) dense helpers on the reduced systems ------------------------------------------------------------------
+
+// cyclic Jacobi: symmetric A (n x n, row-major, n <= 9) = V diag(w) V^T
+template <int N>
+void sym_eig(const double* Ain, double* w, double* V) {
+  double A[N * N];
+  std::memcpy(A, Ain, sizeof(A));
+  for (int i = 0; i < N; ++i)
+    for (int j = 0; j < N; ++j) V[i * N + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < N; ++i) {
+      dg += A[i * N + i] * A[i * N + i];
+      for (int j = i + 1; j < N; ++j) off += A[i * N + j] * A[i * N + j];
+    }
+    if (off <= 1e-60 || off <= 1e-34 * dg) break;
+    for (int p = 0; p < N - 1; ++p)
+      for (int q = p + 1; q < N; ++q) {
+        const double apq = A[p * N + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q * N + q] - A[p * N + p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < N; ++k) {
+          const double a = A[k * N + p], b = A[k * N + q];
+          A[k * N + p] = c * a - s * b;
+          A[k * N + q] = s * a + c * b;
+        }
+        for (int k = 0; k < N; ++k) {
+          const double a = A[p * N + k], b = A[q * N + k];
+          A[p * N + k] = c * a - s * b;
+          A[q * N + k] = s * a + c * b;
+        }
+        for (int k = 0; k < N; ++k) {
+          const double a = V[k * N + p], b = V[k * N + q];
+          V[k * N + p] = c * a - s * b;
+          V[k * N + q] = s * a + c * b;
+        }
+      }
+  }
+  for (int i = 0; i < N; ++i) w[i] = A[i * N + i];
+}
+
+template <int N>
+void sym_singular_values(const double* A, double* sv) {
+  double w[N], V[N * N];
+  sym_eig<N>(A, w, V);
+  for (int i = 0; i < N; ++i) sv[i] = std::fabs(w[i]);
+  std::sort(sv, sv + N, [](double a, double b) { return a > b; });
+}
+
+// LDL^T with diagonal pivoting for the positive semi-definite 9x9 of the closed form
+void ldlt9_solve(const double* Ain, const double* bin, double* x) {
+  constexpr int n = 9;
+  double A[81], b[9];
+  int perm[9];
+  std::memcpy(A, Ain, sizeof(A));
+  std::memcpy(b, bin, sizeof(b));
+  for (int i = 0; i < n; ++i) perm[i] = i;
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < n; ++i)
+      if (std::fabs(A[i * n + i]) > std::fabs(A[piv * n + piv])) piv = i;
+    if (piv != k) {
+      for (int j = 0; j < n; ++j) std::swap(A[k * n + j], A[piv * n + j]);
+      for (int j = 0; j < n; ++j) std::swap(A[j * n + k], A[j * n + piv]);
+      std::swap(b[k], b[piv]);
+      std::swap(perm[k], perm[piv]);
+    }
+    const double d = A[k * n + k];
+    if (d == 0.0) continue;
+    for (int i = k + 1; i < n; ++i) {
+      const double l = A[i * n + k] / d;
+      for (int j = k + 1; j < n; ++j) A[i * n + j] -= l * A[k * n + j];
+      A[i * n + k] = l;
+    }
+  }
+  double z[9], y[9];
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= A[i * n + k] * z[k];
+    z[i] = s;
+  }
+  for (int i = 0; i < n; ++i) z[i] = (A[i * n + i] != 0.0) ? z[i] / A[i * n + i] : 0.0;
+  for (int i = n - 1; i >= 0; --i) {
+    double s = z[i];
+    for (int k = i + 1; k < n; ++k) s -= A[k * n + i] * y[k];
+    y[i] = s;
+  }
+  for (int i = 0; i < n; ++i) x[perm[i]] = y[i];
+}
+
+int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+// ---- the problem object -----------------------------------------------------------------------------------------
+struct clc_problem {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+  int grid = 0;
+  int64_t n_frames = 0, n_points = 0, n_points_padded = 0, n_edges = 0;
+  int use_loss = 1;
+  double cauchy_a = 0.05;
+  // device buffers
+  double *x = nullptr, *y = nullptr, *z = nullptr;
+  double* frame_pose = nullptr;
+  double* plane = nullptr;
+  int64_t* offsets = nullptr;
+  int* warp_first_frame = nullptr;
+  double* edge_plane = nullptr;
+  double* edge_pt = nullptr;
+  double* partials = nullptr;
+  double* sums = nullptr;
+  double* pose = nullptr;
+  unsigned int* ticket = nullptr;
+  clc::LmState* lm = nullptr;
+  double* flush_buf = nullptr;
+  int64_t flush_n = 0;
+  // pinned host mirrors
+  double* h_sums = nullptr;
+  int* h_done = nullptr;
+  clc::LmState* h_lm = nullptr;
+  // communicator
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  int allreduce_mode = 0;
+  int64_t per_warp = 0;
+};
+
+namespace {
+
+clc::ProblemView make_view(const clc_problem* p) {
+  clc::ProblemView v;
+  v.x = p->x; v.y = p->y; v.z = p->z;
+  v.plane = p->plane;
+  v.offsets = p->offsets;
+  v.warp_first_frame = p->warp_first_frame;
+  v.edge_plane = p->edge_plane;
+  v.edge_pt = p->edge_pt;
+  v.n_frames = p->n_frames;
+  v.n_points = p->n_points;
+  v.n_edges = p->n_edges;
+  v.per_warp = p->per_warp;
+  v.a2 = p->cauchy_a * p->cauchy_a;
+  v.inv_a2 = 1.0 / v.a2;
+  return v;
+}
+
+int set_device(const clc_problem* p) {
+  CLC_CUDA(cudaSetDevice(p->device));
+  return CLC_OK;
+}
+
+// one K1 launch on the problem's stream
+int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* d_pose, const int* d_done,
+                 clc::LmState* d_lm) {
+  clc::SweepArgs a;
+  a.pose7 = d_pose;
+  a.done = d_done;
+  a.partials = p->partials;
+  a.sums = p->sums;
+  a.ticket = p->ticket;
+  a.lm = d_lm;
+  a.use_loss = loss ? 1 : 0;
+  a.use_edges = edges ? 1 : 0;
+  const clc::ProblemView v = make_view(p);
+  if (mode == clc::kModeClosedForm) {
+    clc::clc_sweep_kernel<false, clc::kModeClosedForm><<<p->grid, clc::kThreads, 0, p->stream>>>(v, a);
+  } else if (loss) {
+    clc::clc_sweep_kernel<true, clc::kModeLM><<<p->grid, clc::kThreads, 0, p->stream>>>(v, a);
+  } else {
+    clc::clc_sweep_kernel<false, clc::kModeLM><<<p->grid, clc::kThreads, 0, p->stream>>>(v, a);
+  }
+  CLC_LAUNCH_CHECK();
+  return CLC_OK;
+}
+
+int allreduce_sums(clc_problem* p, int count) {
+  if (p->nranks <= 1) return CLC_OK;
+  CLC_NCCL(nccl_api()->AllReduce(p->sums, p->sums, (size_t)count, ncclDouble, ncclSum, p->comm, p->stream));
+  return CLC_OK;
+}
+
+// common tail of the two create paths: planes, warp table, work buffers
+int finish_create(clc_problem* p) {
+  const int threads = 256;
+  if (p->n_frames > 0) {
+    const int blocks = (int)((p->n_frames + threads - 1) / threads);
+    clc::clc_planes_kernel<<<blocks, threads, 0, p->stream>>>(p->frame_pose, p->n_frames, p->plane, p->edge_plane);
+    CLC_LAUNCH_CHECK();
+  }
+  // persistent grid: SM count x resident blocks per SM (the smallest occupancy of the instantiations used)
+  int occ = 0, occ_min = 1 << 30;
+  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<true, clc::kModeLM>, clc::kThreads, 0));
+  occ_min = std::min(occ_min, occ);
+  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeLM>, clc::kThreads, 0));
+  occ_min = std::min(occ_min, occ);
+  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeClosedForm>, clc::kThreads, 0));
+  occ_min = std::min(occ_min, occ);
+  int blocks_per_sm = std::max(1, occ_min);
+  if (const char* env = std::getenv("CLC_BLOCKS_PER_SM")) {
+    const int v = std::atoi(env);
+    if (v >= 1) blocks_per_sm = std::min(v, std::max(1, occ_min));
+  }
+  p->grid = p->num_sms * blocks_per_sm;
+  const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
+  p->per_warp = std::max<int64_t>(clc::kGroup, round_up((p->n_points + n_warps - 1) / n_warps, clc::kGroup));
+  CLC_CUDA(cudaMalloc(&p->warp_first_frame, sizeof(int) * n_warps));
+  {
+    const int blocks = (int)((n_warps + threads - 1) / threads);
+    clc::clc_warp_table_kernel<<<blocks, threads, 0, p->stream>>>(p->offsets, p->n_frames, p->n_points, p->per_warp,
+                                                                  n_warps, p->warp_first_frame);
+    CLC_LAUNCH_CHECK();
+  }
+  CLC_CUDA(cudaMalloc(&p->partials, sizeof(double) * (size_t)p->grid * clc::kMaxOut));
+  CLC_CUDA(cudaMalloc(&p->sums, sizeof(double) * clc::kMaxOut));
+  CLC_CUDA(cudaMalloc(&p->pose, sizeof(double) * 8));
+  CLC_CUDA(cudaMalloc(&p->ticket, sizeof(unsigned int)));
+  CLC_CUDA(cudaMalloc(&p->lm, sizeof(clc::LmState)));
+  CLC_CUDA(cudaMemsetAsync(p->ticket, 0, sizeof(unsigned int), p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->sums, 0, sizeof(double) * clc::kMaxOut, p->stream));
+  CLC_CUDA(cudaMallocHost(&p->h_sums, sizeof(double) * clc::kMaxOut));
+  CLC_CUDA(cudaMallocHost(&p->h_done, sizeof(int)));
+  CLC_CUDA(cudaMallocHost(&p->h_lm, sizeof(clc::LmState)));
+  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  return CLC_OK;
+}
+
+int init_device(clc_problem* p, int device) {
+  int count = 0;
+  CLC_CUDA(cudaGetDeviceCount(&count));
+  if (count <= 0) return fail(CLC_ERR_CUDA, "no CUDA device");
+  if (device < 0) CLC_CUDA(cudaGetDevice(&device));
+  if (device >= count) return fail(CLC_ERR_INVALID, "device ordinal out of range");
+  p->device = device;
+  CLC_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CLC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(CLC_ERR_CUDA, std::string("libclc_b200 is built for sm_100a only; device is sm_") +
+                                  std::to_string(prop.major) + std::to_string(prop.minor));
+  p->num_sms = prop.multiProcessorCount;
+  CLC_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+  return CLC_OK;
+}
+
+int alloc_points(clc_problem* p) {
+  p->n_points_padded = round_up(p->n_points, clc::kGroup) + 2 * clc::kGroup;
+  const size_t bytes = sizeof(double) * (size_t)p->n_points_padded;
+  CLC_CUDA(cudaMalloc(&p->x, bytes));
+  CLC_CUDA(cudaMalloc(&p->y, bytes));
+  CLC_CUDA(cudaMalloc(&p->z, bytes));
+  // zero the padding (finite values are required beyond the last point)
+  const int64_t tail = p->n_points_padded - p->n_points;
+  CLC_CUDA(cudaMemsetAsync(p->x + p->n_points, 0, sizeof(double) * tail, p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->y + p->n_points, 0, sizeof(double) * tail, p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->z + p->n_points, 0, sizeof(double) * tail, p->stream));
+  return CLC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* clc_last_error(void) { return g_last_error.c_str(); }
+
+int clc_device_count(int* count) {
+  if (!count) return fail(CLC_ERR_INVALID, "count is NULL");
+  CLC_CUDA(cudaGetDeviceCount(count));
+  return CLC_OK;
+}
+
+int64_t clc_launch_count(void) { return g_launches.load(); }
+
+void clc_lm_default_options(clc_lm_options* o) {
+  o->max_num_iterations = 100;  // reference src/LaseCamCalCeres.cpp:304
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1;
+  o->iterations_per_sync = 8;
+  o->reserved = 0;
+}
+
+void clc_T_to_pose7(const double T[16], double pose7[7]) {
+  const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+  clc::rot_to_quat(R, pose7 + 3);
+  pose7[0] = T[3]; pose7[1] = T[7]; pose7[2] = T[11];
+}
+
+void clc_pose7_to_T(const double pose7[7], double T[16]) {
+  double R[9];
+  clc::quat_to_rot(pose7 + 3, R);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) T[r * 4 + c] = R[r * 3 + c];
+    T[r * 4 + 3] = pose7[r];
+  }
+  T[12] = T[13] = T[14] = 0.0;
+  T[15] = 1.0;
+}
+
+int clc_problem_destroy(clc_problem* p) {
+  if (!p) return CLC_OK;
+  cudaSetDevice(p->device);
+  if (p->stream) cudaStreamSynchronize(p->stream);
+  if (p->comm && nccl_api()->handle) nccl_api()->CommDestroy(p->comm);
+  cudaFree(p->x); cudaFree(p->y); cudaFree(p->z);
+  cudaFree(p->frame_pose); cudaFree(p->plane); cudaFree(p->offsets); cudaFree(p->warp_first_frame);
+  cudaFree(p->edge_plane); cudaFree(p->edge_pt); cudaFree(p->partials); cudaFree(p->sums); cudaFree(p->pose);
+  cudaFree(p->ticket); cudaFree(p->lm); cudaFree(p->flush_buf);
+  cudaFreeHost(p->h_sums); cudaFreeHost(p->h_done); cudaFreeHost(p->h_lm);
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+  return CLC_OK;
+}
+
+int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
+  if (!out || !d) return fail(CLC_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (d->n_frames < 0 || (d->n_frames > 0 && (!d->frame_pose || !d->offsets)))
+    return fail(CLC_ERR_INVALID, "frame_pose/offsets missing");
+  if (!(d->cauchy_a > 0.0)) return fail(CLC_ERR_INVALID, "cauchy_a must be positive");
+  const int64_t N = d->n_frames;
+  const int64_t P = N > 0 ? d->offsets[N] : 0;
+  if (N > 0 && d->offsets[0] != 0) return fail(CLC_ERR_INVALID, "offsets[0] must be 0");
+  for (int64_t f = 0; f < N; ++f)
+    if (d->offsets[f + 1] < d->offsets[f]) return fail(CLC_ERR_INVALID, "offsets must be non-decreasing");
+  if (P > 0 && !d->points) return fail(CLC_ERR_INVALID, "points missing");
+  if (N >= ((int64_t)1 << 31)) return fail(CLC_ERR_INVALID, "too many frames");
+
+  clc_problem* p = new clc_problem();
+  int rc = init_device(p, d->device);
+  if (rc != CLC_OK) { clc_problem_destroy(p); return rc; }
+  p->n_frames = N;
+  p->n_points = P;
+  p->n_edges = d->edge_points ? 2 * N : 0;
+  p->use_loss = d->use_loss;
+  p->cauchy_a = d->cauchy_a;
+  auto body = [&]() -> int {
+    int rc2 = alloc_points(p);
+    if (rc2 != CLC_OK) return rc2;
+    CLC_CUDA(cudaMalloc(&p->frame_pose, sizeof(double) * 7 * std::max<int64_t>(N, 1)));
+    CLC_CUDA(cudaMalloc(&p->plane, sizeof(double) * 4 * std::max<int64_t>(N, 1)));
+    CLC_CUDA(cudaMalloc(&p->offsets, sizeof(int64_t) * (N + 1)));
+    if (N > 0) {
+      CLC_CUDA(cudaMemcpyAsync(p->frame_pose, d->frame_pose, sizeof(double) * 7 * N, cudaMemcpyHostToDevice, p->stream));
+      CLC_CUDA(cudaMemcpyAsync(p->offsets, d->offsets, sizeof(int64_t) * (N + 1), cudaMemcpyHostToDevice, p->stream));
+    } else {
+      CLC_CUDA(cudaMemsetAsync(p->offsets, 0, sizeof(int64_t), p->stream));
+    }
+    if (p->n_edges > 0) {
+      CLC_CUDA(cudaMalloc(&p->edge_plane, sizeof(double) * 4 * p->n_edges));
+      CLC_CUDA(cudaMalloc(&p->edge_pt, sizeof(double) * 3 * p->n_edges));
+      // [n_frames*6] front,back == [n_edges*3]
+      CLC_CUDA(cudaMemcpyAsync(p->edge_pt, d->edge_points, sizeof(double) * 3 * p->n_edges, cudaMemcpyHostToDevice, p->stream));
+    }
+    // points: AoS on the host -> staged in chunks -> SoA in HBM
+    if (P > 0) {
+      const int64_t chunk = std::min<int64_t>(P, (int64_t)8 << 20);  // 8 Mi points = 192 MiB of AoS per stage
+      double* stage = nullptr;
+      CLC_CUDA(cudaMalloc(&stage, sizeof(double) * 3 * chunk));
+      int status = CLC_OK;
+      for (int64_t b = 0; b < P && status == CLC_OK; b += chunk) {
+        const int64_t n = std::min(chunk, P - b);
+        cudaError_t e = cudaMemcpyAsync(stage, d->points + 3 * b, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, p->stream);
+        if (e != cudaSuccess) { status = fail(CLC_ERR_CUDA, cudaGetErrorString(e)); break; }
+        clc::clc_aos_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(stage, n, p->x, p->y, p->z, b);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) status = fail(CLC_ERR_CUDA, cudaGetErrorString(e));
+      }
+      cudaStreamSynchronize(p->stream);
+      cudaFree(stage);
+      if (status != CLC_OK) return status;
+    }
+    return finish_create(p);
+  };
+  rc = body();
+  if (rc != CLC_OK) { clc_problem_destroy(p); return rc; }
+  *out = p;
+  return CLC_OK;
+}
+
+int clc_problem_create_synthetic(clc_problem** out, const clc_synthetic_desc* d) {
+  if (!out || !d) return fail(CLC_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (d->frame_begin < 0 || d->frame_end < d->frame_begin || d->frame_end > d->n_frames_total || d->beams <= 0)
+    return fail(CLC_ERR_INVALID, "bad frame range / beams");
+  if (!(d->cauchy_a > 0.0)) return fail(CLC_ERR_INVALID, "cauchy_a must be positive");
+  const int64_t N = d->frame_end - d->frame_begin;
+  if (N >= ((int64_t)1 << 31)) return fail(CLC_ERR_INVALID, "too many frames");
+  clc_problem* p = new clc_problem();
+  int rc = init_device(p, d->device);
+  if (rc != CLC_OK) { clc_problem_destroy(p); return rc; }
+  p->n_frames = N;
+  p->n_points = N * d->beams;
+  p->n_edges = d->with_edges ? 2 * N : 0;
+  p->use_loss = d->use_loss;
+  p->cauchy_a = d->cauchy_a;
+  auto body = [&]() -> int {
+    int rc2 = alloc_points(p);
+    if (rc2 != CLC_OK) return rc2;
+    CLC_CUDA(cudaMalloc(&p->frame_pose, sizeof(double) * 7 * std::max<int64_t>(N, 1)));
+    CLC_CUDA(cudaMalloc(&p->plane, sizeof(double) * 4 * std::max<int64_t>(N, 1)));
+    CLC_CUDA(cudaMalloc(&p->offsets, sizeof(int64_t) * (N + 1)));
+    if (p->n_edges > 0) {
+      CLC_CUDA(cudaMalloc(&p->edge_plane, sizeof(double) * 4 * p->n_edges));
+      CLC_CUDA(cudaMalloc(&p->edge_pt, sizeof(double) * 3 * p->n_edges));
+    }
+    if (N > 0) {
+      clc::clc_gen_frames_kernel<<<(unsigned)((N + 127) / 128), 128, 0, p->stream>>>(
+          d->seed, d->frame_begin, N, d->beams, d->with_edges, p->frame_pose, p->offsets, p->edge_pt);
+      CLC_LAUNCH_CHECK();
+      clc::clc_gen_points_kernel<<<(unsigned)N, 256, 0, p->stream>>>(d->seed, d->sigma, d->frame_begin, d->beams,
+                                                                    p->frame_pose, p->x, p->y, p->z);
+      CLC_LAUNCH_CHECK();
+    } else {
+      CLC_CUDA(cudaMemsetAsync(p->offsets, 0, sizeof(int64_t), p->stream));
+    }
+    return finish_create(p);
+  };
+  rc = body();
+  if (rc != CLC_OK) { clc_problem_destroy(p); return rc; }
+  *out = p;
+  return CLC_OK;
+}
+
+int clc_problem_sizes(const clc_problem* p, int64_t* n_frames, int64_t* n_points, int* has_edges) {
+  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
+  if (n_frames) *n_frames = p->n_frames;
+  if (n_points) *n_points = p->n_points;
+  if (has_edges) *has_edges = p->n_edges > 0;
+  return CLC_OK;
+}
+
+int clc_problem_algorithmic_bytes(const clc_problem* p, int64_t* bytes) {
+  if (!p || !bytes) return fail(CLC_ERR_INVALID, "NULL argument");
+  *bytes = 24 * p->n_points + 40 * p->n_frames + 56 * p->n_edges + 224;
+  return CLC_OK;
+}
+
+int clc_problem_download(const clc_problem* p, double* frame_pose, int64_t* offsets, double* points,
+                         double* edge_points, double* planes) {
+  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  if (frame_pose && p->n_frames > 0)
+    CLC_CUDA(cudaMemcpy(frame_pose, p->frame_pose, sizeof(double) * 7 * p->n_frames, cudaMemcpyDeviceToHost));
+  if (offsets) CLC_CUDA(cudaMemcpy(offsets, p->offsets, sizeof(int64_t) * (p->n_frames + 1), cudaMemcpyDeviceToHost));
+  if (planes && p->n_frames > 0)
+    CLC_CUDA(cudaMemcpy(planes, p->plane, sizeof(double) * 4 * p->n_frames, cudaMemcpyDeviceToHost));
+  if (edge_points && p->n_edges > 0)
+    CLC_CUDA(cudaMemcpy(edge_points, p->edge_pt, sizeof(double) * 3 * p->n_edges, cudaMemcpyDeviceToHost));
+  if (points && p->n_points > 0) {
+    double* aos = nullptr;
+    CLC_CUDA(cudaMalloc(&aos, sizeof(double) * 3 * p->n_points));
+    clc::clc_soa_to_aos_kernel<<<(unsigned)((p->n_points + 255) / 256), 256, 0, p->stream>>>(p->x, p->y, p->z, 0,
+                                                                                          p->n_points, aos);
+    g_launches.fetch_add(1);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(points, aos, sizeof(double) * 3 * p->n_points, cudaMemcpyDeviceToHost, p->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+    cudaFree(aos);
+    if (e != cudaSuccess) return fail(CLC_ERR_CUDA, cudaGetErrorString(e));
+  }
+  return CLC_OK;
+}
+
+// ---- evaluation -------------------------------------------------------------------------------------------------
+
+static int eval_common(clc_problem* p, const double pose7[7], bool loss, bool edges, int mode, int count) {
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  if (mode == clc::kModeLM) {
+    if (!pose7) return fail(CLC_ERR_INVALID, "pose7 is NULL");
+    CLC_CUDA(cudaMemcpyAsync(p->pose, pose7, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
+  } else {
+    const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+    CLC_CUDA(cudaMemcpyAsync(p->pose, ident, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
+  }
+  rc = launch_sweep(p, mode, loss, edges, p->pose, nullptr, nullptr);
+  if (rc != CLC_OK) return rc;
+  rc = allreduce_sums(p, count);
+  if (rc != CLC_OK) return rc;
+  CLC_CUDA(cudaMemcpyAsync(p->h_sums, p->sums, sizeof(double) * count, cudaMemcpyDeviceToHost, p->stream));
+  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  return CLC_OK;
+}
+
+static void unpack_H(const double* sums, double* H36) {
+  int k = 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = i; j < 6; ++j) {
+      H36[i * 6 + j] = sums[k];
+      H36[j * 6 + i] = sums[k];
+      ++k;
+    }
+}
+
+int clc_eval(clc_problem* p, const double pose7[7], double H36[36], double g6[6], double* cost) {
+  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
+  int rc = eval_common(p, pose7, p->use_loss != 0, p->n_edges > 0, clc::kModeLM, clc::kNumSums);
+  if (rc != CLC_OK) return rc;
+  if (H36) unpack_H(p->h_sums, H36);
+  if (g6) for (int i = 0; i < 6; ++i) g6[i] = p->h_sums[21 + i];
+  if (cost) *cost = p->h_sums[27];
+  return CLC_OK;
+}
+
+int clc_information(clc_problem* p, const double pose7[7], double H36[36], double b6[6], double* chi, double sv6[6]) {
+  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
+  // reference :318-381: no loss, no edge residuals, scale kept
+  int rc = eval_common(p, pose7, false, false, clc::kModeLM, clc::kNumSums);
+  if (rc != CLC_OK) return rc;
+  double H[36];
+  unpack_H(p->h_sums, H);
+  if (H36) std::memcpy(H36, H, sizeof(H));
+  if (b6) for (int i = 0; i < 6; ++i) b6[i] = -p->h_sums[21 + i];
+  if (chi) *chi = 2.0 * p->h_sums[27];
+  if (sv6) sym_singular_values<6>(H, sv6);
+  return CLC_OK;
+}
+
+int clc_closed_form(clc_problem* p, double Tlc[16], int* unobservable, double AtA81[81], double Atb9[9]) {
+  if (!p || !Tlc) return fail(CLC_ERR_INVALID, "NULL argument");
+  int rc = eval_common(p, nullptr, false, false, clc::kModeClosedForm, clc::kMaxOut);
+  if (rc != CLC_OK) return rc;
+  double AtA[81], Atb[9];
+  int k = 0;
+  for (int i = 0; i < 9; ++i)
+    for (int j = i; j < 9; ++j) {
+      AtA[i * 9 + j] = p->h_sums[k];
+      AtA[j * 9 + i] = p->h_sums[k];
+      ++k;
+    }
+  for (int i = 0; i < 9; ++i) Atb[i] = p->h_sums[45 + i];
+  if (AtA81) std::memcpy(AtA81, AtA, sizeof(AtA));
+  if (Atb9) std::memcpy(Atb9, Atb, sizeof(Atb));
+  double sv[9];
+  sym_singular_values<9>(AtA, sv);
+  int unobs = 0;
+  for (int i = 0; i < 9; ++i)
+    if (sv[i] < 1e-10) unobs = 1;  // reference :165-171
+  if (unobservable) *unobservable = unobs;
+  double h[9];
+  ldlt9_solve(AtA, Atb, h);  // reference :181
+  const double* h1 = h;
+  const double* h2 = h + 3;
+  const double* h3 = h + 6;
+  double h12[3];
+  clc::cross3(h1, h2, h12);
+  // Rlc = [h1 h2 h1xh2]^T (rows), tlc = -Rlc h3 before orthogonalisation (reference :187-192)
+  const double Rlc[9] = {h1[0], h1[1], h1[2], h2[0], h2[1], h2[2], h12[0], h12[1], h12[2]};
+  double tlc[3];
+  for (int r = 0; r < 3; ++r) tlc[r] = -(Rlc[r * 3] * h3[0] + Rlc[r * 3 + 1] * h3[1] + Rlc[r * 3 + 2] * h3[2]);
+  // U V^T of Rlc (reference :195-196) = Rlc (Rlc^T Rlc)^(-1/2); no determinant check, as in the reference
+  double G[9], w[3], V[9], S[9], Ro[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) G[i * 3 + j] = Rlc[i] * Rlc[j] + Rlc[3 + i] * Rlc[3 + j] + Rlc[6 + i] * Rlc[6 + j];
+  sym_eig<3>(G, w, V);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int q = 0; q < 3; ++q) s += V[i * 3 + q] * (1.0 / std::sqrt(w[q])) * V[j * 3 + q];
+      S[i * 3 + j] = s;
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) Ro[i * 3 + j] = Rlc[i * 3] * S[j] + Rlc[i * 3 + 1] * S[3 + j] + Rlc[i * 3 + 2] * S[6 + j];
+  for (int i = 0; i < 16; ++i) Tlc[i] = 0.0;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) Tlc[r * 4 + c] = Ro[r * 3 + c];
+    Tlc[r * 4 + 3] = tlc[r];
+  }
+  Tlc[15] = 1.0;
+  return CLC_OK;
+}
+
+// ---- the on-device LM solve ------------------------------------------------------------------------------------
+
+int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, clc_lm_summary* summary,
+                 clc_lm_iteration* trace, int trace_cap) {
+  if (!p || !pose7) return fail(CLC_ERR_INVALID, "NULL argument");
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  clc_lm_options opt;
+  if (opt_in) opt = *opt_in; else clc_lm_default_options(&opt);
+  if (opt.max_num_iterations < 0) return fail(CLC_ERR_INVALID, "max_num_iterations < 0");
+  if (opt.iterations_per_sync < 1) opt.iterations_per_sync = 1;
+
+  clc::lm_init(p->h_lm, pose7, opt);
+  cudaEvent_t ev0, ev1;
+  CLC_CUDA(cudaEventCreate(&ev0));
+  CLC_CUDA(cudaEventCreate(&ev1));
+  CLC_CUDA(cudaMemcpyAsync(p->lm, p->h_lm, sizeof(clc::LmState), cudaMemcpyHostToDevice, p->stream));
+  CLC_CUDA(cudaEventRecord(ev0, p->stream));
+  const bool fused_update = (p->nranks <= 1);
+  const bool loss = p->use_loss != 0, edges = p->n_edges > 0;
+  // every LM iteration needs exactly one sweep; invalid steps need none -> at most max_iterations + 1 sweeps
+  const int max_sweeps = opt.max_num_iterations + 2;
+  int launched = 0;
+  *p->h_done = 0;
+  while (launched < max_sweeps) {
+    const int batch = std::min(opt.iterations_per_sync, max_sweeps - launched);
+    for (int i = 0; i < batch; ++i) {
+      rc = launch_sweep(p, clc::kModeLM, loss, edges, p->lm->cand, &p->lm->done, fused_update ? p->lm : nullptr);
+      if (rc != CLC_OK) return rc;
+      if (!fused_update) {
+        rc = allreduce_sums(p, clc::kNumSums);
+        if (rc != CLC_OK) return rc;
+        clc::clc_lm_kernel<<<1, 32, 0, p->stream>>>(p->lm, p->sums);
+        CLC_LAUNCH_CHECK();
+      }
+    }
+    launched += batch;
+    CLC_CUDA(cudaMemcpyAsync(p->h_done, &p->lm->done, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CLC_CUDA(cudaStreamSynchronize(p->stream));
+    if (*p->h_done != 0) break;
+  }
+  CLC_CUDA(cudaEventRecord(ev1, p->stream));
+  CLC_CUDA(cudaMemcpyAsync(p->h_lm, p->lm, sizeof(clc::LmState), cudaMemcpyDeviceToHost, p->stream));
+  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  float ms = 0.f;
+  CLC_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+
+  const clc::LmState& s = *p->h_lm;
+  for (int i = 0; i < 7; ++i) pose7[i] = s.x[i];  // the last accepted point (a terminating candidate is not applied)
+  if (summary) {
+    summary->termination = s.done ? s.done : CLC_TERM_NO_CONVERGENCE;
+    summary->num_iterations = s.n_trace;
+    summary->num_successful_steps = s.num_successful;
+    summary->num_unsuccessful_steps = s.num_unsuccessful;
+    summary->num_sweeps = s.sweeps;
+    summary->reserved = 0;
+    summary->initial_cost = s.initial_cost;
+    summary->final_cost = s.x_cost;
+    summary->device_ms = ms;
+  }
+  if (trace) {
+    const int n = std::min(std::min(s.n_trace, clc::kTraceMax), trace_cap);
+    for (int i = 0; i < n; ++i) trace[i] = s.trace[i];
+  }
+  return CLC_OK;
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------------------------
+
+int clc_shard_range(int64_t n_frames, const int64_t* offsets, int nranks, int rank, int64_t* begin, int64_t* end) {
+  if (nranks < 1 || rank < 0 || rank >= nranks || n_frames < 0 || !begin || !end)
+    return fail(CLC_ERR_INVALID, "bad shard arguments");
+  if (!offsets) {
+    *begin = n_frames * rank / nranks;
+    *end = n_frames * (rank + 1) / nranks;
+    return CLC_OK;
+  }
+  // contiguous ranges balanced by point count: boundary r is the first frame whose start >= r * P / nranks
+  const int64_t P = offsets[n_frames];
+  auto boundary = [&](int r) -> int64_t {
+    if (r <= 0) return 0;
+    if (r >= nranks) return n_frames;
+    const int64_t target = (int64_t)((__int128)P * r / nranks);
+    return std::lower_bound(offsets, offsets + n_frames + 1, target) - offsets;
+  };
+  *begin = boundary(rank);
+  *end = boundary(rank + 1);
+  if (*end < *begin) *end = *begin;
+  return CLC_OK;
+}
+
+int clc_comm_unique_id(void* id128) {
+  if (!id128) return fail(CLC_ERR_INVALID, "NULL id");
+  NcclApi* api = nccl_api();
+  if (!api->handle) return fail(CLC_ERR_NCCL, api->error);
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  CLC_NCCL(api->GetUniqueId(&id));
+  std::memcpy(id128, &id, sizeof(id));
+  return CLC_OK;
+}
+
+int clc_problem_attach_comm(clc_problem* p, const void* id128, int nranks, int rank) {
+  if (!p || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(CLC_ERR_INVALID, "bad comm arguments");
+  if (p->comm) return fail(CLC_ERR_STATE, "communicator already attached");
+  NcclApi* api = nccl_api();
+  if (!api->handle) return fail(CLC_ERR_NCCL, api->error);
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  CLC_NCCL(api->CommInitRank(&p->comm, nranks, id, rank));
+  p->nranks = nranks;
+  p->rank = rank;
+  return CLC_OK;
+}
+
+int clc_problem_set_allreduce_mode(clc_problem* p, int mode) {
+  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
+  if (mode != 0) return fail(CLC_ERR_INVALID, "unknown all-reduce mode");
+  p->allreduce_mode = mode;
+  return CLC_OK;
+}
+
+// ---- measurement hooks -------------------------------------------------------------------------------------------
+
+int clc_bench_eval(clc_problem* p, const double pose7[7], int n, int flush_l2, float* ms_each) {
+  if (!p || !pose7 || n < 1 || !ms_each) return fail(CLC_ERR_INVALID, "bad bench arguments");
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  if (flush_l2 && !p->flush_buf) {
+    p->flush_n = ((int64_t)256 << 20) / sizeof(double);  // 256 MiB > 126 MB of L2
+    CLC_CUDA(cudaMalloc(&p->flush_buf, sizeof(double) * p->flush_n));
+  }
+  CLC_CUDA(cudaMemcpyAsync(p->pose, pose7, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
+  std::vector<cudaEvent_t> ev(2 * (size_t)n);
+  for (auto& e : ev) CLC_CUDA(cudaEventCreate(&e));
+  const bool loss = p->use_loss != 0, edges = p->n_edges > 0;
+  for (int i = 0; i < n; ++i) {
+    if (flush_l2) {
+      clc::clc_flush_kernel<<<p->num_sms * 4, 256, 0, p->stream>>>(p->flush_buf, p->flush_n, (double)i);
+      CLC_LAUNCH_CHECK();
+    }
+    CLC_CUDA(cudaEventRecord(ev[2 * i], p->stream));
+    rc = launch_sweep(p, clc::kModeLM, loss, edges, p->pose, nullptr, nullptr);
+    if (rc != CLC_OK) return rc;
+    CLC_CUDA(cudaEventRecord(ev[2 * i + 1], p->stream));
+  }
+  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  for (int i = 0; i < n; ++i) CLC_CUDA(cudaEventElapsedTime(&ms_each[i], ev[2 * i], ev[2 * i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  return CLC_OK;
+}
+
+int clc_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes < 0) return fail(CLC_ERR_INVALID, "bad host alloc arguments");
+  CLC_CUDA(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 1)));
+  return CLC_OK;
+}
+
+int clc_host_free(void* ptr) {
+  if (ptr) CLC_CUDA(cudaFreeHost(ptr));
+  return CLC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,480 @@
+// clc_kernels.cuh -- the sm_100a kernels.
+//
+// K1  clc_sweep_kernel   fused residual + Jacobian + Cauchy weight + reduce over every laser point
+//                        (HBM-bandwidth bound FP64 map-reduce; 24 B per residual streamed with 128-bit loads)
+// K3  clc_lm_kernel      single-thread LM update (multi-rank path, after the all-reduce)
+// K0  layout kernels     AoS -> SoA, frame pose -> board plane / edge planes, warp start table
+// K5  generator kernels  synthetic boards on the device
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "clc_expand.cuh"
+#include "clc_lm.cuh"
+
+namespace clc {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTileStride = 13;       // doubles per tile row: 10 moments, product, exponent, frame id
+constexpr int kGroup = 64;            // points per warp iteration (2 per lane, one LDG.128 per array)
+constexpr int kMaxOut = 54;           // closed-form mode: 45 + 9
+
+enum SweepMode { kModeLM = 0, kModeClosedForm = 1 };
+
+// Device-resident problem (read-only for the sweeps).
+struct ProblemView {
+  const double* x;            // SoA coordinates, zero padded to a multiple of kGroup (+ kGroup)
+  const double* y;
+  const double* z;
+  const double* plane;        // [n_frames*4]   n, d in the camera frame
+  const int64_t* offsets;     // [n_frames+1]
+  const int* warp_first_frame;  // [total warps of the launch grid] frame containing each warp's first point
+  const double* edge_plane;   // [n_edges*4] or nullptr
+  const double* edge_pt;      // [n_edges*3]
+  int64_t n_frames;
+  int64_t n_points;
+  int64_t n_edges;            // 2 * n_frames or 0
+  int64_t per_warp;           // points per warp (multiple of kGroup)
+  double inv_a2;              // 1 / cauchy_a^2
+  double a2;                  // cauchy_a^2
+};
+
+struct SweepArgs {
+  const double* pose7;        // device pointer: the pose to evaluate
+  const int* done;            // device flag: non-zero -> the sweep is a no-op (LM finished); may be nullptr
+  double* partials;           // [gridDim.x * kMaxOut]
+  double* sums;               // [kMaxOut] result of the launch
+  unsigned int* ticket;       // last-block-done counter (self-resetting)
+  LmState* lm;                // non-null: the last block also runs lm_update (single-rank fused mode)
+  int use_loss;
+  int use_edges;
+};
+
+// ---- small device helpers ---------------------------------------------------------------------------------
+
+__device__ __forceinline__ double2 ldg_stream2(const double* p) {
+  // 128-bit read-only load; data is touched once per sweep -> do not pollute L1
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// 1/a for a normal, positive a: MUFU.RCP64H seed (2^-23 relative) + two Newton steps (-> ~1 ulp).
+__device__ __forceinline__ double rcp_pos(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Per-lane streaming accumulators of one piece.
+struct Moments {
+  double S0, Sx, Sy, Sz, Sxx, Sxy, Sxz, Syy, Syz, Szz;
+  double prod;  // loss on: running product of (1 + e^2/a^2), mantissa kept in [1,2); loss off: running sum of e^2
+  int esum;     // exponent taken out of prod
+};
+
+template <bool LOSS>
+__device__ __forceinline__ void moments_clear(Moments& a) {
+  a.S0 = a.Sx = a.Sy = a.Sz = a.Sxx = a.Sxy = a.Sxz = a.Syy = a.Syz = a.Szz = 0.0;
+  a.prod = LOSS ? 1.0 : 0.0;
+  a.esum = 0;
+}
+
+__device__ __forceinline__ void accumulate(Moments& a, double w, double x, double y, double z) {
+  const double wx = w * x, wy = w * y, wz = w * z;
+  a.S0 += w;
+  a.Sx += wx; a.Sy += wy; a.Sz += wz;
+  a.Sxx = fma(wx, x, a.Sxx); a.Sxy = fma(wx, y, a.Sxy); a.Sxz = fma(wx, z, a.Sxz);
+  a.Syy = fma(wy, y, a.Syy); a.Syz = fma(wy, z, a.Syz); a.Szz = fma(wz, z, a.Szz);
+}
+
+// Two points (one LDG.128 per coordinate array).  v0/v1: validity of the two points.
+template <bool LOSS, bool COST>
+__device__ __forceinline__ void process2(Moments& a, const double2 X, const double2 Y, const double2 Z, bool v0,
+                                         bool v1, double m0, double m1, double m2, double c, double inv_a2) {
+  const double e0 = fma(m0, X.x, fma(m1, Y.x, fma(m2, Z.x, c)));
+  const double e1 = fma(m0, X.y, fma(m1, Y.y, fma(m2, Z.y, c)));
+  if (LOSS) {
+    double u0 = fma(e0 * inv_a2, e0, 1.0);
+    double u1 = fma(e1 * inv_a2, e1, 1.0);
+    u0 = v0 ? u0 : 1.0;
+    u1 = v1 ? u1 : 1.0;
+    // batch inversion: one reciprocal of u0*u1 serves both weights and the cost product
+    const double p = u0 * u1;
+    const double r = rcp_pos(p);
+    double w0 = r * u1, w1 = r * u0;
+    w0 = v0 ? w0 : 0.0;
+    w1 = v1 ? w1 : 0.0;
+    a.prod *= p;
+    accumulate(a, w0, X.x, Y.x, Z.x);
+    accumulate(a, w1, X.y, Y.y, Z.y);
+  } else {
+    if (COST) {
+      a.prod = fma(v0 ? e0 : 0.0, e0, a.prod);
+      a.prod = fma(v1 ? e1 : 0.0, e1, a.prod);
+    }
+    accumulate(a, v0 ? 1.0 : 0.0, X.x, Y.x, Z.x);
+    accumulate(a, v1 ? 1.0 : 0.0, X.y, Y.y, Z.y);
+  }
+}
+
+__device__ __forceinline__ void renormalise(Moments& a) {
+  // prod >= 1: move its binary exponent into esum (exact)
+  const int hi = __double2hiint(a.prod);
+  const int ex = (hi >> 20) - 1023;
+  a.esum += ex;
+  a.prod = __hiloint2double(hi - (ex << 20), __double2loint(a.prod));
+}
+
+// ---- K1: the fused sweep -------------------------------------------------------------------------------------
+//
+// Work decomposition: the P points are cut into equal contiguous ranges, one per warp of a grid that fills the
+// machine exactly once (persistent, SM-count x occupancy blocks).  A warp walks its range frame piece by frame
+// piece; within a piece each lane streams 2 points per 128-bit load triple and keeps 10 weighted moments plus
+// the running cost product in registers.  At the end of a piece the lanes' moments are summed by warp shuffles
+// and parked in a shared-memory tile; every 32 pieces (and at the end) the tile is expanded -- one piece per
+// lane -- into the 28 normal-equation sums, which are shuffle-reduced and added to the warp's accumulator in
+// shared memory.  Block partials go to global memory; the last block to finish (ticket) adds them in a fixed
+// order, so the result is bit-reproducible from run to run, and optionally runs the LM update.
+template <bool LOSS, int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+clc_sweep_kernel(ProblemView pv, SweepArgs args) {
+  constexpr int NOUT = (MODE == kModeLM) ? kNumSums : kMaxOut;
+  __shared__ double s_tile[kWarps][32 * kTileStride];
+  __shared__ double s_acc[kWarps][NOUT];
+  __shared__ double s_red[kWarps][32];
+  __shared__ bool s_last;
+
+  if (args.done != nullptr && *args.done != 0) return;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t gwarp = (int64_t)blockIdx.x * kWarps + warp;
+
+  for (int k = lane; k < NOUT; k += 32) s_acc[warp][k] = 0.0;
+
+  PoseConsts pc;
+  {
+    double pose[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pose[i] = args.pose7[i];
+    make_pose_consts(pose, &pc);
+  }
+
+  double* tile = s_tile[warp];
+  int n_tile = 0;
+
+  // expands the parked pieces (one per lane) and folds them into the warp accumulator
+  auto flush_tile = [&]() {
+    double out[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) out[k] = 0.0;
+    __syncwarp();
+    if (lane < n_tile) {
+      const double* row = tile + lane * kTileStride;
+      const int64_t f = __double_as_longlong(row[12]);
+      double plane[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) plane[k] = pv.plane[f * 4 + k];
+      if (MODE == kModeLM) {
+        double m[3], c;
+        frame_consts(pc, plane, m, &c);
+        const double cnt = (double)(pv.offsets[f + 1] - pv.offsets[f]);
+        double cost_term = row[10];  // loss off: sum e^2
+        if (LOSS) cost_term = log(row[10]) + row[11] * 0.693147180559945309417232121458;
+        expand_lm(plane, m, c, 1.0 / cnt, row, LOSS, cost_term, pv.a2, out);
+      } else {
+        expand_closed_form(plane, row, out);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+      const double v = warp_sum(out[k]);
+      if (lane == 0) s_acc[warp][k] += v;
+    }
+    __syncwarp();
+    n_tile = 0;
+  };
+
+  // ---- main stream over this warp's point range ----
+  const int64_t P = pv.n_points;
+  int64_t p = gwarp * pv.per_warp;
+  if (p > P) p = P;
+  int64_t p_end = p + pv.per_warp;
+  if (p_end > P) p_end = P;
+  if (p < p_end) {
+    int64_t f = pv.warp_first_frame[gwarp];
+    while (p < p_end) {
+      const int64_t f_end = pv.offsets[f + 1];
+      if (f_end <= p) { ++f; continue; }
+      const int64_t pe = f_end < p_end ? f_end : p_end;
+      // frame constants (every lane, redundantly)
+      double m0, m1, m2, c;
+      {
+        double plane[4], m[3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) plane[k] = pv.plane[f * 4 + k];
+        frame_consts(pc, plane, m, &c);
+        m0 = m[0]; m1 = m[1]; m2 = m[2];
+      }
+      Moments a;
+      moments_clear<LOSS>(a);
+      // lanes take points (k, k+1); k is even so the 128-bit loads are aligned
+      int64_t k = (p & ~(int64_t)1) + 2 * lane;
+      for (; k + kGroup < pe; k += 2 * kGroup) {
+        // two groups in flight: 6 independent LDG.128 per lane
+        const double2 X0 = ldg_stream2(pv.x + k), Y0 = ldg_stream2(pv.y + k), Z0 = ldg_stream2(pv.z + k);
+        const double2 X1 = ldg_stream2(pv.x + k + kGroup), Y1 = ldg_stream2(pv.y + k + kGroup),
+                      Z1 = ldg_stream2(pv.z + k + kGroup);
+        process2<LOSS, MODE == kModeLM>(a, X0, Y0, Z0, k >= p, true, m0, m1, m2, c, pv.inv_a2);
+        process2<LOSS, MODE == kModeLM>(a, X1, Y1, Z1, true, k + kGroup + 1 < pe, m0, m1, m2, c, pv.inv_a2);
+        if (LOSS) renormalise(a);
+      }
+      if (k < pe) {
+        const double2 X0 = ldg_stream2(pv.x + k), Y0 = ldg_stream2(pv.y + k), Z0 = ldg_stream2(pv.z + k);
+        process2<LOSS, MODE == kModeLM>(a, X0, Y0, Z0, k >= p, k + 1 < pe, m0, m1, m2, c, pv.inv_a2);
+        if (LOSS) renormalise(a);
+      }
+      // ---- piece reduction over the 32 lanes ----
+      const double r0 = warp_sum(a.S0), r1 = warp_sum(a.Sx), r2 = warp_sum(a.Sy), r3 = warp_sum(a.Sz);
+      const double r4 = warp_sum(a.Sxx), r5 = warp_sum(a.Sxy), r6 = warp_sum(a.Sxz);
+      const double r7 = warp_sum(a.Syy), r8 = warp_sum(a.Syz), r9 = warp_sum(a.Szz);
+      double pr = a.prod;
+      int es = a.esum;
+      if (LOSS) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          pr *= __shfl_xor_sync(0xffffffffu, pr, o);  // 32 mantissas in [1,2): product < 2^32
+          es += __shfl_xor_sync(0xffffffffu, es, o);
+        }
+      } else {
+        pr = warp_sum(pr);
+      }
+      if (lane == 0) {
+        double* row = tile + n_tile * kTileStride;
+        row[0] = r0; row[1] = r1; row[2] = r2; row[3] = r3; row[4] = r4; row[5] = r5; row[6] = r6;
+        row[7] = r7; row[8] = r8; row[9] = r9; row[10] = pr; row[11] = (double)es;
+        row[12] = __longlong_as_double(f);
+      }
+      ++n_tile;
+      if (n_tile == 32) flush_tile();
+      p = pe;
+      if (pe == f_end) ++f;
+    }
+  }
+  flush_tile();
+
+  // ---- board-edge residuals: one residual per lane, same moment/expansion path ----
+  if (MODE == kModeLM && args.use_edges && pv.n_edges > 0) {
+    const int64_t total_lanes = (int64_t)gridDim.x * kThreads;
+    double out[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) out[k] = 0.0;
+    bool any = false;
+    for (int64_t i = gwarp * 32 + lane; i < pv.n_edges; i += total_lanes) {
+      const int64_t f = i >> 1;
+      const int64_t cnt = pv.offsets[f + 1] - pv.offsets[f];
+      if (cnt <= 0) continue;
+      any = true;
+      double plane[4], m[3], c;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) plane[k] = pv.edge_plane[i * 4 + k];
+      frame_consts(pc, plane, m, &c);
+      const double x = pv.edge_pt[i * 3], y = pv.edge_pt[i * 3 + 1], z = pv.edge_pt[i * 3 + 2];
+      const double e = fma(m[0], x, fma(m[1], y, fma(m[2], z, c)));
+      double w = 1.0, cost_term = e * e;
+      if (LOSS) {
+        const double u = fma(e * pv.inv_a2, e, 1.0);
+        w = 1.0 / u;
+        cost_term = log(u);
+      }
+      const double S[10] = {w, w * x, w * y, w * z, w * x * x, w * x * y, w * x * z, w * y * y, w * y * z, w * z * z};
+      expand_lm(plane, m, c, 1.0 / (double)cnt, S, LOSS, cost_term, pv.a2, out);
+    }
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        const double v = warp_sum(out[k]);
+        if (lane == 0) s_acc[warp][k] += v;
+      }
+    }
+  }
+
+  // ---- block reduction (fixed order) ----
+  __syncthreads();
+  if (threadIdx.x < NOUT) {
+    double v = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kWarps; ++wv) v += s_acc[wv][threadIdx.x];
+    args.partials[(int64_t)blockIdx.x * kMaxOut + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(args.ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+
+  // ---- last block: deterministic sum of the block partials ----
+  __threadfence();
+  {
+    // warp wv sums blocks wv, wv+8, ...; lane handles output `lane` (and lane+32 for the 54-wide mode)
+    for (int k = lane; k < NOUT; k += 32) {
+      double v = 0.0;
+      for (int b = warp; b < (int)gridDim.x; b += kWarps) v += __ldcg(args.partials + (int64_t)b * kMaxOut + k);
+      if (k < 32) s_red[warp][k] = v; else s_acc[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NOUT) {
+      double v = 0.0;
+      const int k = threadIdx.x;
+#pragma unroll
+      for (int wv = 0; wv < kWarps; ++wv) v += (k < 32) ? s_red[wv][k] : s_acc[wv][k];
+      args.sums[k] = v;
+      if (k < 32) s_red[0][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *args.ticket = 0u;
+      if (MODE == kModeLM && args.lm != nullptr) {
+        double sums[kNumSums];
+        for (int k = 0; k < kNumSums; ++k) sums[k] = s_red[0][k];
+        lm_update(args.lm, sums);
+      }
+    }
+  }
+}
+
+// ---- K3: LM update as its own launch (multi-rank: runs after the all-reduce of `sums`) --------------------------
+__global__ void clc_lm_kernel(LmState* lm, const double* sums) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s[kNumSums];
+    for (int k = 0; k < kNumSums; ++k) s[k] = sums[k];
+    lm_update(lm, s);
+  }
+}
+
+// ---- K0: layout kernels ------------------------------------------------------------------------------------------
+
+// AoS (x,y,z)[n] -> SoA at element offset `dst_off`
+__global__ void clc_aos_to_soa_kernel(const double* __restrict__ aos, int64_t n, double* __restrict__ x,
+                                      double* __restrict__ y, double* __restrict__ z, int64_t dst_off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    x[dst_off + i] = aos[3 * i];
+    y[dst_off + i] = aos[3 * i + 1];
+    z[dst_off + i] = aos[3 * i + 2];
+  }
+}
+
+__global__ void clc_soa_to_aos_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                      const double* __restrict__ z, int64_t src_off, int64_t n,
+                                      double* __restrict__ aos) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    aos[3 * i] = x[src_off + i];
+    aos[3 * i + 1] = y[src_off + i];
+    aos[3 * i + 2] = z[src_off + i];
+  }
+}
+
+// frame pose -> board plane (a2) and the two edge planes (a7)
+__global__ void clc_planes_kernel(const double* __restrict__ frame_pose, int64_t n_frames, double* __restrict__ plane,
+                                  double* __restrict__ edge_plane) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  double fp[7], pl[4];
+  for (int k = 0; k < 7; ++k) fp[k] = frame_pose[f * 7 + k];
+  frame_plane(fp, pl);
+  for (int k = 0; k < 4; ++k) plane[f * 4 + k] = pl[k];
+  if (edge_plane != nullptr) {
+    double p1[4], p2[4];
+    edge_planes(fp, p1, p2);
+    for (int k = 0; k < 4; ++k) {
+      edge_plane[(2 * f) * 4 + k] = p1[k];
+      edge_plane[(2 * f + 1) * 4 + k] = p2[k];
+    }
+  }
+}
+
+// frame containing the first point of every warp range (binary search done once at problem creation)
+__global__ void clc_warp_table_kernel(const int64_t* __restrict__ offsets, int64_t n_frames, int64_t n_points,
+                                      int64_t per_warp, int64_t n_warps, int* __restrict__ first_frame) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_warps) return;
+  const int64_t p0 = w * per_warp;
+  if (p0 >= n_points) { first_frame[w] = 0; return; }
+  int64_t lo = 0, hi = n_frames;  // offsets[lo] <= p0 < offsets[hi]
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (offsets[mid] <= p0) lo = mid; else hi = mid;
+  }
+  first_frame[w] = (int)lo;
+}
+
+// ---- K5: synthetic generator (exact-M mode) ----------------------------------------------------------------------
+
+__global__ void clc_gen_frames_kernel(uint64_t seed, int64_t frame_begin, int64_t n_local, int64_t beams, int with_edges,
+                                      double* __restrict__ frame_pose, int64_t* __restrict__ offsets,
+                                      double* __restrict__ edge_pt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) offsets[n_local] = n_local * beams;
+  if (i >= n_local) return;
+  double fp[7];
+  gen_frame_pose(seed, frame_begin + i, with_edges != 0, fp);
+  for (int k = 0; k < 7; ++k) frame_pose[i * 7 + k] = fp[k];
+  offsets[i] = i * beams;
+  if (with_edges) {
+    double ep[6];
+    if (!gen_edge_points(fp, ep))
+      for (int k = 0; k < 6; ++k) ep[k] = 0.0;
+    for (int k = 0; k < 6; ++k) edge_pt[i * 6 + k] = ep[k];
+  }
+}
+
+// one block per frame
+__global__ void clc_gen_points_kernel(uint64_t seed, double sigma, int64_t frame_begin, int64_t beams,
+                                      const double* __restrict__ frame_pose, double* __restrict__ x,
+                                      double* __restrict__ y, double* __restrict__ z) {
+  const int64_t i = blockIdx.x;
+  __shared__ double s_nl[3], s_dl, s_a, s_b;
+  if (threadIdx.x == 0) {
+    double fp[7], nl[3], dl, a = 0.0, b = 0.0;
+    for (int k = 0; k < 7; ++k) fp[k] = frame_pose[i * 7 + k];
+    gen_plane_laser(fp, nl, &dl);
+    gen_window(nl, dl, &a, &b);
+    s_nl[0] = nl[0]; s_nl[1] = nl[1]; s_nl[2] = nl[2]; s_dl = dl; s_a = a; s_b = b;
+  }
+  __syncthreads();
+  const double n0 = s_nl[0], n1 = s_nl[1], dl = s_dl, a = s_a, b = s_b;
+  for (int64_t j = threadIdx.x; j < beams; j += blockDim.x) {
+    const double theta = a + (b - a) * (((double)j + 0.5) / (double)beams);
+    const double cx = cos(theta), sy = sin(theta);
+    const double depth = -dl / (cx * n0 + sy * n1) + gen_noise(seed, sigma, frame_begin + i, j);
+    const int64_t o = i * beams + j;
+    x[o] = depth * cx;
+    y[o] = depth * sy;
+    z[o] = 0.0;
+  }
+}
+
+// L2 flush for the measurement hook: overwrite a buffer larger than L2
+__global__ void clc_flush_kernel(double* buf, int64_t n, double v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    buf[i] = v;
+}
+
+}  // namespace clc

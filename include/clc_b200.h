@@ -1,0 +1,189 @@
+/*
+ * clc_b200.h -- C ABI of libclc_b200.so: the B200-native (sm_100a) implementation of the camera<-laser
+ * extrinsic solve of MegviiRobot/CamLaserCalibraTool.
+ *
+ * The reference has no FFI: its "operator API" for this path is four C++ free functions plus one struct
+ * (reference include/LaseCamCalCeres.h:11-29).  This header is the boundary a replacement of
+ * reference src/LaseCamCalCeres.cpp binds to; camlasercalibratool_b200/host/LaseCamCalB200.cpp is that
+ * replacement (same signatures, same Oberserve struct) and INTEGRATION.md shows the CMake change.
+ *
+ * Plain C, POD only, int status codes (0 = CLC_OK), no exceptions cross the boundary, no torch types.
+ * There is NO CPU fallback: every entry point fails with CLC_ERR_CUDA if no sm_100 device is usable.
+ *
+ * Data conventions (identical to the marshalled form of std::vector<Oberserve>):
+ *   frame_pose[f*7 .. +7] = qx,qy,qz,qw (Eigen coeff order of Oberserve::tagPose_Qca), tx,ty,tz (tagPose_tca)
+ *                           -- reference include/LaseCamCalCeres.h:20-21
+ *   offsets[n_frames+1]   = CSR delimiters of the frames inside `points`
+ *   points[P*3]           = AoS x,y,z doubles: the calibration point set the reference selects at
+ *                           src/LaseCamCalCeres.cpp:233-237 (obs.points or obs.points_on_line)
+ *   edge_points[f*6..+6]  = obs[f].points.front() then obs[f].points.back() (src/LaseCamCalCeres.cpp:278-279);
+ *                           non-NULL enables the board-edge residuals of :258-294
+ *   pose7                 = tx,ty,tz,qx,qy,qz,qw: the Ceres parameter block of T_cl (:219)
+ *   4x4 matrices are row-major.
+ */
+#ifndef CLC_B200_H
+#define CLC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLC_OK 0
+#define CLC_ERR_INVALID 1  /* bad argument */
+#define CLC_ERR_CUDA 2     /* CUDA runtime / no usable device */
+#define CLC_ERR_NCCL 3     /* NCCL missing or a collective failed */
+#define CLC_ERR_STATE 4    /* call not valid in this state */
+
+typedef struct clc_problem clc_problem; /* opaque, device-resident problem (one per GPU / rank) */
+
+/* replaces: the argument marshalling of CamLaserCalibration()/CamLaserCalClosedSolution(),
+ * reference src/LaseCamCalCeres.cpp:213-295 and :112-159 */
+typedef struct {
+  int64_t n_frames;
+  const double* frame_pose;  /* host [n_frames*7] */
+  const int64_t* offsets;    /* host [n_frames+1] */
+  const double* points;      /* host [offsets[n_frames]*3]; pinned memory uploads at full PCIe rate */
+  const double* edge_points; /* host [n_frames*6] or NULL */
+  int use_loss;              /* 1: CauchyLoss(cauchy_a*scale), reference :212,:249 */
+  double cauchy_a;           /* 0.05 */
+  int device;                /* CUDA ordinal, -1 = current device */
+} clc_problem_desc;
+
+/* replaces: GenerateSimData(), reference main/calibr_simulation.cpp:10-108, scaled to n_frames x beams and run
+ * on the device (the 48 GB of BASELINE config 4 cannot pass through std::vector<Oberserve>). */
+typedef struct {
+  int64_t n_frames_total; /* frames of the whole (all-rank) problem; RNG counters are global frame ids */
+  int64_t frame_begin;    /* this problem holds frames [frame_begin, frame_end) */
+  int64_t frame_end;
+  int64_t beams;          /* points per frame (exact-M mode: every frame has exactly `beams` points) */
+  uint64_t seed;
+  double sigma;           /* range noise along the ray, metres */
+  int with_edges;         /* also generate the two board-edge residual points per frame */
+  int use_loss;
+  double cauchy_a;
+  int device;
+} clc_synthetic_desc;
+
+/* Ceres Solver::Options subset, defaults = reference src/LaseCamCalCeres.cpp:302-304 + Ceres defaults */
+typedef struct {
+  int max_num_iterations;           /* 100 */
+  double initial_trust_region_radius; /* 1e4 */
+  double max_trust_region_radius;   /* 1e16 */
+  double min_trust_region_radius;   /* 1e-32 */
+  double min_relative_decrease;     /* 1e-3 */
+  double min_lm_diagonal;           /* 1e-6 */
+  double max_lm_diagonal;           /* 1e32 */
+  double function_tolerance;        /* 1e-6 */
+  double gradient_tolerance;        /* 1e-10 */
+  double parameter_tolerance;       /* 1e-8 */
+  int max_num_consecutive_invalid_steps; /* 5 */
+  int jacobi_scaling;               /* 1 */
+  int iterations_per_sync;          /* LM iterations enqueued between host polls of the device `done` flag (8) */
+  int reserved;
+} clc_lm_options;
+
+/* termination codes (Ceres TerminationType + the tolerance that fired) */
+#define CLC_TERM_RUNNING 0
+#define CLC_TERM_CONVERGENCE_FUNCTION 1
+#define CLC_TERM_CONVERGENCE_PARAMETER 2
+#define CLC_TERM_CONVERGENCE_GRADIENT 3
+#define CLC_TERM_CONVERGENCE_MIN_RADIUS 4
+#define CLC_TERM_NO_CONVERGENCE 5
+#define CLC_TERM_FAILURE 6
+
+/* one row of Ceres' IterationSummary */
+typedef struct {
+  int iteration;
+  int step_is_valid;
+  int step_is_successful;
+  int reserved;
+  double cost;
+  double cost_change;
+  double gradient_max_norm;
+  double step_norm;
+  double relative_decrease;
+  double trust_region_radius;
+} clc_lm_iteration;
+
+typedef struct {
+  int termination;
+  int num_iterations;          /* rows written to the trace (iteration 0 included) */
+  int num_successful_steps;
+  int num_unsuccessful_steps;
+  int num_sweeps;              /* launches of the fused residual+Jacobian+reduce kernel that did work */
+  int reserved;
+  double initial_cost;
+  double final_cost;
+  double device_ms;            /* CUDA-event time of the whole on-device solve on this rank */
+} clc_lm_summary;
+
+const char* clc_last_error(void);
+int clc_device_count(int* count);
+
+void clc_lm_default_options(clc_lm_options* opt);
+
+/* Uploads (H2D) and lays the problem out in HBM (SoA points, per-frame planes).  replaces: problem assembly,
+ * reference src/LaseCamCalCeres.cpp:222-295 (no per-residual heap objects are created). */
+int clc_problem_create(clc_problem** out, const clc_problem_desc* desc);
+/* Same, generated on the device. */
+int clc_problem_create_synthetic(clc_problem** out, const clc_synthetic_desc* desc);
+int clc_problem_destroy(clc_problem* p);
+
+/* Sizes and read-back (tests / the C++ simulation driver). Any output pointer may be NULL. */
+int clc_problem_sizes(const clc_problem* p, int64_t* n_frames, int64_t* n_points, int* has_edges);
+int clc_problem_download(const clc_problem* p, double* frame_pose, int64_t* offsets, double* points,
+                         double* edge_points, double* planes /* [n_frames*4] n,d in the camera frame */);
+
+/* THE FUSED KERNEL (K1): one sweep over every residual at `pose7` -> H = sum J~^T J~ (row-major 6x6),
+ * g = sum J~^T r~, cost = 1/2 sum rho, with the Cauchy correction applied.  All-reduced over the ranks when a
+ * communicator is attached.  replaces: one ceres Evaluate over all PointInPlaneFactor residual blocks,
+ * reference src/LaseCamCalCeres.cpp:43-66 + Ceres Corrector.  Synchronous.  H36/g6 may be NULL. */
+int clc_eval(clc_problem* p, const double pose7[7], double H36[36], double g6[6], double* cost);
+
+/* replaces: ceres::Solve() at reference src/LaseCamCalCeres.cpp:306-307 with the options of :302-304.
+ * pose7 is in/out.  trace may be NULL.  Collective over the communicator's ranks. */
+int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt, clc_lm_summary* summary,
+                 clc_lm_iteration* trace, int trace_cap);
+
+/* replaces: the analysis tail, reference src/LaseCamCalCeres.cpp:318-381: un-robustified H, b = -J^T r,
+ * chi = sum r^2 (scale kept, no edge residuals), singular values of H (descending). */
+int clc_information(clc_problem* p, const double pose7[7], double H36[36], double b6[6], double* chi,
+                    double singular_values6[6]);
+
+/* replaces: CamLaserCalClosedSolution(), reference src/LaseCamCalCeres.cpp:112-203.  Tlc16 row-major.
+ * AtA81/Atb9 (the 9x9 normal equations) may be NULL. */
+int clc_closed_form(clc_problem* p, double Tlc16[16], int* unobservable, double AtA81[81], double Atb9[9]);
+
+/* Eigen-equivalent conversions used on both sides of the boundary (reference :215-219 and :311-314). */
+void clc_T_to_pose7(const double T16[16], double pose7[7]);
+void clc_pose7_to_T(const double pose7[7], double T16[16]);
+
+/* ---- multi-GPU: one process per GPU, frames sharded by the caller, 28-double all-reduce per sweep ---------- */
+/* Balanced contiguous frame range of `rank` (by point count when offsets != NULL, else by frame count). */
+int clc_shard_range(int64_t n_frames, const int64_t* offsets, int nranks, int rank, int64_t* begin, int64_t* end);
+/* NCCL bootstrap: rank 0 calls clc_comm_unique_id, ships the 128 bytes to every rank by any means
+ * (torch.distributed, MPI, a file), then every rank attaches it to its problem. */
+int clc_comm_unique_id(void* id128);
+int clc_problem_attach_comm(clc_problem* p, const void* id128, int nranks, int rank);
+/* all-reduce mode: 0 = ncclAllReduce on the solve stream between the kernels (default) */
+int clc_problem_set_allreduce_mode(clc_problem* p, int mode);
+
+/* ---- measurement hooks (bench.py) ---------------------------------------------------------------------- */
+/* Launches K1 `n` times at pose7 on the problem's stream; each launch is bracketed by its own CUDA events.
+ * flush_l2 != 0 overwrites a buffer larger than L2 between launches (outside the timed brackets).
+ * ms_each[n] receives the per-launch device times.  No collective, local shard only. */
+int clc_bench_eval(clc_problem* p, const double pose7[7], int n, int flush_l2, float* ms_each);
+/* Algorithmic bytes of one K1 launch on this problem: 24*P + 40*N + 56*edges + 224. */
+int clc_problem_algorithmic_bytes(const clc_problem* p, int64_t* bytes);
+/* Pinned host memory for upload buffers. */
+int clc_host_alloc(void** ptr, int64_t bytes);
+int clc_host_free(void* ptr);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t clc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLC_B200_H */

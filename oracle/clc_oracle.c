@@ -613,6 +613,14 @@ int oracle_solve(const oracle_problem* p, double pose7[7], const oracle_options*
   oracle_iteration it;
   memset(&it, 0, sizeof(it));
   EVAL_WITH_JACOBIAN(1);
+  if (!isfinite(x_cost)) {
+    /* Ceres: residual_block.cc IsArrayValid -> "Residual and Jacobian evaluation failed" -> FAILURE */
+    sm.termination = ORACLE_TERM_FAILURE;
+    sm.initial_cost = sm.final_cost = x_cost;
+    if (summary) *summary = sm;
+    if (qr) { free(st.residuals); free(st.jacobian); free(st.qr_A); free(st.qr_b); }
+    return 0;
+  }
   it.iteration = 0;
   it.cost = x_cost;
   it.gradient_max_norm = gradient_max_norm(x, gradient);
@@ -715,6 +723,7 @@ int oracle_solve(const oracle_problem* p, double pose7[7], const oracle_options*
     if (qr) oracle_evaluate(p, cand, &cand_cost, NULL, NULL, NULL, opt->num_threads);
     else oracle_evaluate_normal(p, cand, &cand_cost, NULL, NULL, opt->num_threads);
     sm.num_residual_evaluations++;
+    if (!isfinite(cand_cost)) cand_cost = DBL_MAX; /* Ceres: "treating it as a step with infinite cost" */
 
     /* ---- Ceres: ParameterToleranceReached ---- */
     {

@@ -1,0 +1,61 @@
+// Test-only harness: compiles the product's host/device (CLC_HD) headers with g++ so that the exact source the GPU
+// runs -- the LM state machine, the moment expansion, the plane and generator math -- can be checked against the
+// oracle on a machine without a GPU.  Never shipped, never linked into libclc_b200.so.
+#include <cstring>
+
+#include "../camlasercalibratool_b200/csrc/clc_expand.cuh"
+#include "../camlasercalibratool_b200/csrc/clc_lm.cuh"
+
+extern "C" {
+
+int harness_lm_state_size() { return (int)sizeof(clc::LmState); }
+void harness_lm_init(void* st, const double* pose7, const clc_lm_options* opt) {
+  clc::lm_init(static_cast<clc::LmState*>(st), pose7, *opt);
+}
+void harness_lm_update(void* st, const double* sums28) { clc::lm_update(static_cast<clc::LmState*>(st), sums28); }
+int harness_lm_done(const void* st) { return static_cast<const clc::LmState*>(st)->done; }
+int harness_lm_ntrace(const void* st) { return static_cast<const clc::LmState*>(st)->n_trace; }
+void harness_lm_cand(const void* st, double* out) { std::memcpy(out, static_cast<const clc::LmState*>(st)->cand, 56); }
+void harness_lm_x(const void* st, double* out) { std::memcpy(out, static_cast<const clc::LmState*>(st)->x, 56); }
+void harness_lm_trace(const void* st, int i, clc_lm_iteration* out) { *out = static_cast<const clc::LmState*>(st)->trace[i]; }
+int harness_lm_sweeps(const void* st) { return static_cast<const clc::LmState*>(st)->sweeps; }
+
+// moments of one piece (computed by the caller) -> the 28 sums, through the same code path as the kernel
+void harness_expand_lm(const double* plane, const double* pose7, double count, const double* S10, int use_loss,
+                       double cost_term, double a2, double* out28) {
+  clc::PoseConsts pc;
+  clc::make_pose_consts(pose7, &pc);
+  double m[3], c;
+  clc::frame_consts(pc, plane, m, &c);
+  clc::expand_lm(plane, m, c, 1.0 / count, S10, use_loss != 0, cost_term, a2, out28);
+}
+void harness_frame_consts(const double* plane, const double* pose7, double* m3, double* c) {
+  clc::PoseConsts pc;
+  clc::make_pose_consts(pose7, &pc);
+  clc::frame_consts(pc, plane, m3, c);
+}
+void harness_expand_closed(const double* plane, const double* S10, double* out54) {
+  clc::expand_closed_form(plane, S10, out54);
+}
+void harness_frame_plane(const double* fp, double* plane) { clc::frame_plane(fp, plane); }
+void harness_edge_planes(const double* fp, double* p1, double* p2) { clc::edge_planes(fp, p1, p2); }
+void harness_pose_plus(const double* x, const double* d, double* xp) { clc::pose_plus(x, d, xp); }
+void harness_philox(uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* out) { clc::philox4x32(seed, lo, hi, out); }
+void harness_gen_frame_pose(uint64_t seed, int64_t frame, int with_edges, double* fp) {
+  clc::gen_frame_pose(seed, frame, with_edges != 0, fp);
+}
+int harness_gen_edge_points(const double* fp, double* ep) { return clc::gen_edge_points(fp, ep) ? 1 : 0; }
+// exact-M points of one frame, as clc_gen_points_kernel computes them
+void harness_gen_points(uint64_t seed, double sigma, int64_t frame, int64_t beams, const double* fp, double* pts) {
+  double nl[3], dl, a = 0.0, b = 0.0;
+  clc::gen_plane_laser(fp, nl, &dl);
+  clc::gen_window(nl, dl, &a, &b);
+  for (int64_t j = 0; j < beams; ++j) {
+    const double theta = a + (b - a) * (((double)j + 0.5) / (double)beams);
+    const double cx = cos(theta), sy = sin(theta);
+    const double depth = -dl / (cx * nl[0] + sy * nl[1]) + clc::gen_noise(seed, sigma, frame, j);
+    pts[3 * j] = depth * cx; pts[3 * j + 1] = depth * sy; pts[3 * j + 2] = 0.0;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,261 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI of libclc_b200.so, against the CPU oracle on
+identical inputs.  Tolerances: (H, g, cost) <= 1e-11 relative at a fixed pose; final T_cl within
+1e-6 rad / 1e-6 m (BASELINE.json north_star) -- in practice the trajectories agree to ~1e-10.
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+from conftest import pack_sums
+
+pytestmark = pytest.mark.gpu
+
+X0 = np.array([0, 0, 0, 0, 0, 0, 1.0])
+TOL_SUMS = 1e-11
+TOL_ANG = 1e-6  # rad  (north_star)
+TOL_T = 1e-6    # m    (north_star)
+
+
+def gpu_problem(p, **kw):
+    from camlasercalibratool_b200 import Problem
+
+    return Problem.from_arrays(p.frame_pose, p.offsets, p.points, p.edge_points, use_loss=p.use_loss, cauchy_a=p.cauchy_a, **kw)
+
+
+def assert_sums_close(got, ref, tol=TOL_SUMS):
+    cost, H, g = got
+    rc, rH, rg = ref
+    scale = np.abs(rH).max()
+    assert abs(cost - rc) <= tol * max(abs(rc), 1e-300), (cost, rc)
+    np.testing.assert_allclose(H, rH, rtol=0, atol=tol * scale)
+    np.testing.assert_allclose(g, rg, rtol=0, atol=tol * scale)
+    assert np.array_equal(H, H.T)
+
+
+def poses(oracle, n=3, seed=0):
+    rng = np.random.default_rng(seed)
+    out = [X0, oracle.ground_truth()[1]]
+    for _ in range(n):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        out.append(np.concatenate([rng.normal(size=3) * 0.5, q]))
+    return out
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_eval_config1_faithful_ragged(oracle, seed):
+    """BASELINE config 1: 50 frames x 180 beams, ragged frames from the reference's validity filter."""
+    p = oracle.generate(50, 180, seed=seed, sigma=0.01)
+    with gpu_problem(p) as g:
+        assert g.sizes() == (50, p.n_points, False)
+        for x in poses(oracle):
+            assert_sums_close(g.eval(x), oracle.evaluate_normal(p, x))
+
+
+@pytest.mark.parametrize("n_frames,beams", [(1, 1), (1, 2), (3, 63), (5, 64), (7, 65), (2, 129), (40, 1000), (3, 5000)])
+def test_eval_piece_boundaries(oracle, n_frames, beams):
+    """Frame sizes around the 64-point warp group / 128-point unroll boundaries, odd starts (unaligned 128-bit loads)."""
+    p = oracle.generate(n_frames, beams, seed=5, sigma=0.02, exact_m=True)
+    with gpu_problem(p) as g:
+        for x in poses(oracle, 1):
+            assert_sums_close(g.eval(x), oracle.evaluate_normal(p, x))
+
+
+def test_eval_ragged_with_empty_and_tiny_frames(oracle):
+    """Empty frames (the reference would produce 1/sqrt(0) and no residuals), 1- and 2-point frames
+    (use_linefitting_data = true gives exactly 2 points per frame), odd offsets everywhere."""
+    rng = np.random.default_rng(11)
+    base = oracle.generate(400, 40, seed=8, sigma=0.01, exact_m=True)
+    counts = rng.choice([0, 0, 1, 2, 2, 3, 7, 31, 40], size=400)
+    keep = np.concatenate([np.arange(base.offsets[f], base.offsets[f] + c) for f, c in enumerate(counts)]).astype(int)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    p = oracle.Problem(base.frame_pose, off, base.points[keep])
+    with gpu_problem(p) as g:
+        for x in poses(oracle, 2):
+            assert_sums_close(g.eval(x), oracle.evaluate_normal(p, x))
+        xs, s, _ = g.solve(X0)
+        xo, so, _ = oracle.solve(p, X0)
+        ang, dt = oracle.pose_error(xs, xo)
+        assert ang < TOL_ANG and dt < TOL_T and s.termination == so.termination
+
+
+def test_eval_z_nonzero_and_nonunit_quaternion(oracle):
+    rng = np.random.default_rng(3)
+    p0 = oracle.generate(20, 100, seed=2, sigma=0.01, exact_m=True)
+    pts = p0.points.copy()
+    pts[:, 2] = rng.normal(size=len(pts)) * 0.3
+    fp = p0.frame_pose.copy()
+    fp[:, :4] *= rng.uniform(0.9, 1.1, size=(20, 1))  # the reference does not normalise tagPose_Qca
+    p = oracle.Problem(fp, p0.offsets, pts)
+    with gpu_problem(p) as g:
+        for x in poses(oracle, 2):
+            assert_sums_close(g.eval(x), oracle.evaluate_normal(p, x))
+        np.testing.assert_allclose(g.download()["planes"], [oracle.frame_plane(f) for f in fp], rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("use_loss", [True, False])
+def test_eval_with_edge_residuals(oracle, use_loss):
+    """BASELINE config 5's residual set at test size: per-frame board-edge constraints (reference :258-294)."""
+    p = oracle.generate(300, 50, seed=4, sigma=0.01, exact_m=True, with_edges=True, use_loss=use_loss)
+    with gpu_problem(p) as g:
+        assert g.sizes()[2]
+        for x in poses(oracle, 2):
+            assert_sums_close(g.eval(x), oracle.evaluate_normal(p, x))
+
+
+def test_eval_is_bit_reproducible(oracle):
+    p = oracle.generate(200, 333, seed=6, sigma=0.01, exact_m=True)
+    with gpu_problem(p) as g:
+        a = pack_sums(*g.eval(X0))
+        for _ in range(5):
+            assert np.array_equal(pack_sums(*g.eval(X0)), a)
+    with gpu_problem(p) as g2:
+        assert np.array_equal(pack_sums(*g2.eval(X0)), a)
+
+
+@pytest.mark.parametrize("case", ["noise_free", "noisy", "edges", "no_loss", "bad_start"])
+def test_solve_matches_the_ceres_restatement(oracle, case):
+    """Full on-device LM vs oracle_solve (DENSE_QR on the materialised Jacobian): same termination reason, same
+    accept/reject sequence, cost trajectory to 1e-9, final T_cl within the north-star tolerance."""
+    kw = dict(noise_free=dict(sigma=0.0), noisy=dict(sigma=0.01), edges=dict(sigma=0.01, with_edges=True, exact_m=True),
+              no_loss=dict(sigma=0.01, use_loss=False), bad_start=dict(sigma=0.02))[case]
+    p = oracle.generate(50, 180, seed=2, **kw)
+    x0 = X0
+    if case == "bad_start":
+        x0 = np.array([3.0, -2.0, 4.0, 0.7, 0.1, -0.7, 0.1])
+        x0[3:] /= np.linalg.norm(x0[3:])
+    with gpu_problem(p) as g:
+        x, s, tr = g.solve(x0)
+    xo, so, tro = oracle.solve(p, x0)
+    ang, dt = oracle.pose_error(x, xo)
+    assert ang < TOL_ANG and dt < TOL_T
+    assert s.termination == so.termination and s.num_iterations == so.num_iterations
+    for a, b in zip(tr, tro):
+        assert (a.iteration, a.step_is_valid, a.step_is_successful) == (b.iteration, b.step_is_valid, b.step_is_successful)
+        assert abs(a.cost - b.cost) <= 1e-9 * abs(b.cost) + 1e-18
+    assert s.num_sweeps <= s.num_iterations  # one sweep per LM iteration
+    if case == "noise_free":
+        ang, dt = oracle.pose_error(x, oracle.ground_truth()[1])
+        assert ang < 1e-9 and dt < 1e-9
+
+
+def test_solve_options_and_edge_cases(oracle):
+    from camlasercalibratool_b200 import default_options
+
+    p = oracle.generate(50, 180, seed=1, sigma=0.01)
+    with gpu_problem(p) as g:
+        x, s, tr = g.solve(X0, default_options(max_num_iterations=3))
+        xo, so, _ = oracle.solve(p, X0, oracle.default_options(max_num_iterations=3))
+        assert s.termination == so.termination == 5 and s.num_iterations == 4
+        assert oracle.pose_error(x, xo)[0] < 1e-9
+        x, s, tr = g.solve(X0, default_options(max_num_iterations=0))
+        assert s.num_iterations == 1 and s.num_sweeps == 1 and np.array_equal(x, X0)
+        # iterations_per_sync must not change the result (host polling granularity only)
+        xa, sa, _ = g.solve(X0, default_options(iterations_per_sync=1))
+        xb, sb, _ = g.solve(X0, default_options(iterations_per_sync=50))
+        assert np.array_equal(xa, xb) and sa.num_iterations == sb.num_iterations
+    # NaN input: evaluation failure at the start point -> FAILURE, pose untouched (Ceres' behaviour)
+    bad = oracle.generate(10, 20, seed=1, exact_m=True)
+    pts = bad.points.copy()
+    pts[17, 1] = np.nan
+    with gpu_problem(oracle.Problem(bad.frame_pose, bad.offsets, pts)) as g:
+        x, s, _ = g.solve(X0)
+        assert s.termination == 6 and np.array_equal(x, X0)
+    # a problem with no points at all
+    with gpu_problem(oracle.Problem(bad.frame_pose[:2], [0, 0, 0], np.zeros((0, 3)))) as g:
+        cost, H, gg = g.eval(X0)
+        assert cost == 0 and not H.any() and not gg.any()
+
+
+def test_information_and_closed_form(oracle):
+    p = oracle.generate(50, 180, seed=3, sigma=0.01)
+    x = oracle.pose_plus(oracle.ground_truth()[1], np.array([0.01, -0.02, 0.005, 0.003, -0.001, 0.002]))
+    with gpu_problem(p) as g:
+        H, b, chi, sv = g.information(x)
+        rH, rb, rchi, rsv = oracle.information(p, x)
+        np.testing.assert_allclose(H, rH, rtol=0, atol=1e-11 * np.abs(rH).max())
+        np.testing.assert_allclose(b, rb, rtol=0, atol=1e-11 * np.abs(rH).max())
+        assert abs(chi - rchi) <= 1e-11 * rchi
+        np.testing.assert_allclose(sv, rsv, rtol=1e-9)
+        T, un, AtA, Atb = g.closed_form()
+        rT, run, rAtA, rAtb = oracle.closed_form(p)
+        assert un == run
+        np.testing.assert_allclose(AtA, rAtA, rtol=0, atol=1e-11 * np.abs(rAtA).max())
+        np.testing.assert_allclose(Atb, rAtb, rtol=0, atol=1e-11 * np.abs(rAtb).max())
+        np.testing.assert_allclose(T, rT, atol=1e-8)
+    # noise-free: the closed form is exactly the ground truth
+    q = oracle.generate(50, 180, seed=3)
+    with gpu_problem(q) as g:
+        T, un, _, _ = g.closed_form()
+        np.testing.assert_allclose(T, oracle.ground_truth()[0], atol=1e-8)
+        assert not un
+
+
+def test_reference_entry_points(oracle):
+    """The mirrored CamLaserCalClosedSolution -> CamLaserCalibration call sequence of calibr_offline.cpp:166-170."""
+    from camlasercalibratool_b200 import CamLaserCalClosedSolution, CamLaserCalibration, Oberserve
+
+    p = oracle.generate(50, 180, seed=1, sigma=0.005)
+    obs = []
+    for f in range(p.n_frames):
+        pts = p.points[p.offsets[f]:p.offsets[f + 1]]
+        obs.append(Oberserve(p.frame_pose[f, :4].copy(), p.frame_pose[f, 4:].copy(), pts, pts))
+    Tlc = np.eye(4)
+    CamLaserCalClosedSolution(obs, Tlc, verbose=False)
+    np.testing.assert_allclose(Tlc, oracle.closed_form(p)[0], atol=1e-8)
+    Tcl = np.linalg.inv(Tlc)
+    rep = CamLaserCalibration(obs, Tcl, False, verbose=False)
+    xo, so, _ = oracle.solve(p, oracle.T_to_pose7(np.linalg.inv(Tlc)))
+    np.testing.assert_allclose(Tcl, oracle.pose7_to_T(xo), atol=1e-8)
+    assert rep["termination"] == oracle.TERMINATION[so.termination]
+    assert abs(rep["chi2"] - oracle.information(p, xo)[2] / 2) < 1e-10
+    gt = oracle.ground_truth()[0]
+    assert np.abs(np.linalg.inv(Tcl) - gt).max() < 5e-3  # 5 mm noise
+
+
+def test_device_generator_matches_the_oracle_generator(oracle):
+    from camlasercalibratool_b200 import Problem
+
+    for edges in (False, True):
+        ref = oracle.generate(300, 96, seed=21, sigma=0.01, exact_m=True, with_edges=edges)
+        with Problem.synthetic(300, 96, seed=21, sigma=0.01, with_edges=edges) as g:
+            d = g.download()
+            np.testing.assert_allclose(d["frame_pose"], ref.frame_pose, rtol=0, atol=1e-14)
+            assert np.array_equal(d["offsets"], ref.offsets)
+            np.testing.assert_allclose(d["points"], ref.points, rtol=0, atol=1e-12)
+            if edges:
+                np.testing.assert_allclose(d["edge_points"], ref.edge_points, rtol=0, atol=1e-12)
+            # evaluated on the device-generated data itself
+            p = oracle.Problem(d["frame_pose"], d["offsets"], d["points"], d["edge_points"])
+            assert_sums_close(g.eval(X0), oracle.evaluate_normal(p, X0))
+        # a shard [100, 200) of the same global problem holds the same frames
+        with Problem.synthetic(300, 96, seed=21, sigma=0.01, with_edges=edges, frame_begin=100, frame_end=200) as g:
+            d2 = g.download()
+            np.testing.assert_allclose(d2["frame_pose"], ref.frame_pose[100:200], rtol=0, atol=1e-14)
+            np.testing.assert_allclose(d2["points"], ref.points[100 * 96:200 * 96], rtol=0, atol=1e-12)
+
+
+def test_full_size_config2_properties(oracle):
+    """BASELINE config 2 at full size (10^4 frames x 10^3 points): size-independent properties.
+    (a) the sums of the shards add up to the sums of the whole (linearity / sharding invariance);
+    (b) noise-free data is solved at the ground truth; (c) a 16-thread oracle sweep agrees."""
+    from camlasercalibratool_b200 import Problem
+
+    N, M = 10000, 1000
+    with Problem.synthetic(N, M, seed=7, sigma=0.01) as g:
+        assert g.algorithmic_bytes() == 24 * N * M + 40 * N + 224
+        x = oracle.pose_plus(oracle.ground_truth()[1], np.array([0.02, -0.01, 0.03, 0.01, -0.02, 0.015]))
+        whole = pack_sums(*g.eval(x))
+        d = g.download()
+    parts = np.zeros(28)
+    for k in range(3):
+        b, e = N * k // 3, N * (k + 1) // 3
+        with Problem.synthetic(N, M, seed=7, sigma=0.01, frame_begin=b, frame_end=e) as gs:
+            parts += pack_sums(*gs.eval(x))
+    np.testing.assert_allclose(parts, whole, rtol=0, atol=1e-11 * np.abs(whole).max())
+    p = oracle.Problem(d["frame_pose"], d["offsets"], d["points"])
+    ref = pack_sums(*oracle.evaluate_normal(p, x, num_threads=16))
+    np.testing.assert_allclose(whole, ref, rtol=0, atol=1e-11 * np.abs(ref).max())
+    with Problem.synthetic(N, M, seed=7, sigma=0.0) as g:
+        xs, s, tr = g.solve(X0)
+        ang, dt = oracle.pose_error(xs, oracle.ground_truth()[1])
+        assert ang < 1e-9 and dt < 1e-9 and s.termination in (1, 2, 3)
