@@ -9,6 +9,7 @@ from .api import (  # noqa: F401
     CamLaserCalClosedSolution,
     CamLaserCalibration,
     ClcError,
+    Comm,
     Oberserve,
     Problem,
     T_to_pose7,
@@ -21,6 +22,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "CamLaserCalClosedSolution", "CamLaserCalibration", "ClcError", "Oberserve", "Problem", "T_to_pose7",
+    "CamLaserCalClosedSolution", "CamLaserCalibration", "ClcError", "Comm", "Oberserve", "Problem", "T_to_pose7",
     "comm_unique_id", "default_options", "launch_count", "marshal", "pose7_to_T", "shard_range",
 ]

@@ -122,7 +122,9 @@ SIGNATURES = {
     "clc_pose7_to_T": (None, [c_double_p, c_double_p]),
     "clc_shard_range": (C.c_int, [C.c_int64, c_int64_p, C.c_int, C.c_int, c_int64_p, c_int64_p]),
     "clc_comm_unique_id": (C.c_int, [_P]),
-    "clc_problem_attach_comm": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "clc_comm_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, C.c_int]),
+    "clc_comm_destroy": (C.c_int, [_P]),
+    "clc_problem_attach_comm": (C.c_int, [_P, _P]),
     "clc_problem_set_allreduce_mode": (C.c_int, [_P, C.c_int]),
     "clc_bench_eval": (C.c_int, [_P, c_double_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "clc_problem_algorithmic_bytes": (C.c_int, [_P, c_int64_p]),

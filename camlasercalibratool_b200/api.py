@@ -77,6 +77,7 @@ class Problem:
     def __init__(self, handle):
         self._h = handle
         self._L = _lib.load()
+        self._comm = None
 
     # ---- construction ----
     @classmethod
@@ -182,9 +183,10 @@ class Problem:
         return T.reshape(4, 4), bool(un.value), AtA, Atb
 
     # ---- multi-GPU ----
-    def attach_comm(self, unique_id: bytes, nranks: int, rank: int):
-        buf = C.create_string_buffer(unique_id, 128)
-        _lib.check(self._L.clc_problem_attach_comm(self._h, buf, int(nranks), int(rank)), "clc_problem_attach_comm")
+    def attach_comm(self, comm: "Comm | None"):
+        """Borrow a communicator: every sweep's 28 sums are then all-reduced over its ranks."""
+        self._comm = comm  # keep it alive
+        _lib.check(self._L.clc_problem_attach_comm(self._h, comm._h if comm is not None else None), "clc_problem_attach_comm")
 
     # ---- measurement ----
     def bench_eval(self, pose7, n, flush_l2=True):
@@ -192,6 +194,28 @@ class Problem:
         ms = (C.c_float * n)()
         _lib.check(self._L.clc_bench_eval(self._h, _dp(pose7), int(n), int(bool(flush_l2)), ms), "clc_bench_eval")
         return np.array(ms[:], dtype=np.float64)
+
+
+class Comm:
+    """NCCL communicator of the solve (one per rank / GPU), shareable between problems on the same device."""
+
+    def __init__(self, unique_id: bytes, nranks: int, rank: int, device: int = -1):
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        _lib.check(self._L.clc_comm_create(C.byref(self._h), buf, int(nranks), int(rank), int(device)), "clc_comm_create")
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    def close(self):
+        if self._h is not None:
+            self._L.clc_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def comm_unique_id() -> bytes:

@@ -182,7 +182,12 @@ int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
-// ---- the problem object -----------------------------------------------------------------------------------------
+// ---- the communicator and problem objects ------------------------------------------------------------------------
+struct clc_comm {
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0, device = 0;
+};
+
 struct clc_problem {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -210,7 +215,7 @@ struct clc_problem {
   double* h_sums = nullptr;
   int* h_done = nullptr;
   clc::LmState* h_lm = nullptr;
-  // communicator
+  // communicator (borrowed)
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
   int allreduce_mode = 0;
@@ -400,7 +405,6 @@ int clc_problem_destroy(clc_problem* p) {
   if (!p) return CLC_OK;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  if (p->comm && nccl_api()->handle) nccl_api()->CommDestroy(p->comm);
   cudaFree(p->x); cudaFree(p->y); cudaFree(p->z);
   cudaFree(p->frame_pose); cudaFree(p->plane); cudaFree(p->offsets); cudaFree(p->warp_first_frame);
   cudaFree(p->edge_plane); cudaFree(p->edge_pt); cudaFree(p->partials); cudaFree(p->sums); cudaFree(p->pose);
@@ -777,18 +781,50 @@ int clc_comm_unique_id(void* id128) {
   return CLC_OK;
 }
 
-int clc_problem_attach_comm(clc_problem* p, const void* id128, int nranks, int rank) {
-  if (!p || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(CLC_ERR_INVALID, "bad comm arguments");
-  if (p->comm) return fail(CLC_ERR_STATE, "communicator already attached");
+int clc_comm_create(clc_comm** out, const void* id128, int nranks, int rank, int device) {
+  if (!out || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(CLC_ERR_INVALID, "bad comm arguments");
+  *out = nullptr;
   NcclApi* api = nccl_api();
   if (!api->handle) return fail(CLC_ERR_NCCL, api->error);
-  int rc = set_device(p);
-  if (rc != CLC_OK) return rc;
+  if (device < 0) CLC_CUDA(cudaGetDevice(&device));
+  CLC_CUDA(cudaSetDevice(device));
   ncclUniqueId id;
   std::memcpy(&id, id128, sizeof(id));
-  CLC_NCCL(api->CommInitRank(&p->comm, nranks, id, rank));
-  p->nranks = nranks;
-  p->rank = rank;
+  clc_comm* c = new clc_comm();
+  c->nranks = nranks;
+  c->rank = rank;
+  c->device = device;
+  ncclResult_t r = api->CommInitRank(&c->comm, nranks, id, rank);
+  if (r != ncclSuccess) {
+    delete c;
+    return fail(CLC_ERR_NCCL, std::string("ncclCommInitRank: ") + api->GetErrorString(r));
+  }
+  *out = c;
+  return CLC_OK;
+}
+
+int clc_comm_destroy(clc_comm* c) {
+  if (!c) return CLC_OK;
+  if (c->comm && nccl_api()->handle) {
+    cudaSetDevice(c->device);
+    nccl_api()->CommDestroy(c->comm);
+  }
+  delete c;
+  return CLC_OK;
+}
+
+int clc_problem_attach_comm(clc_problem* p, clc_comm* c) {
+  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
+  if (!c) {
+    p->comm = nullptr;
+    p->nranks = 1;
+    p->rank = 0;
+    return CLC_OK;
+  }
+  if (c->device != p->device) return fail(CLC_ERR_INVALID, "communicator and problem live on different devices");
+  p->comm = c->comm;
+  p->nranks = c->nranks;
+  p->rank = c->rank;
   return CLC_OK;
 }
 

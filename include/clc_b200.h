@@ -164,9 +164,14 @@ void clc_pose7_to_T(const double pose7[7], double T16[16]);
 /* Balanced contiguous frame range of `rank` (by point count when offsets != NULL, else by frame count). */
 int clc_shard_range(int64_t n_frames, const int64_t* offsets, int nranks, int rank, int64_t* begin, int64_t* end);
 /* NCCL bootstrap: rank 0 calls clc_comm_unique_id, ships the 128 bytes to every rank by any means
- * (torch.distributed, MPI, a file), then every rank attaches it to its problem. */
+ * (torch.distributed, MPI, a file); every rank creates its communicator (collective) and attaches it to any number
+ * of problems on that device.  The communicator is borrowed: it must outlive the problems it is attached to.
+ * Attaching NULL detaches. */
+typedef struct clc_comm clc_comm;
 int clc_comm_unique_id(void* id128);
-int clc_problem_attach_comm(clc_problem* p, const void* id128, int nranks, int rank);
+int clc_comm_create(clc_comm** out, const void* id128, int nranks, int rank, int device);
+int clc_comm_destroy(clc_comm* comm);
+int clc_problem_attach_comm(clc_problem* p, clc_comm* comm);
 /* all-reduce mode: 0 = ncclAllReduce on the solve stream between the kernels (default) */
 int clc_problem_set_allreduce_mode(clc_problem* p, int mode);
 

@@ -387,9 +387,9 @@ int oracle_evaluate_normal(const oracle_problem* p, const double pose7[7], doubl
 /* Dense helpers                                                                                          */
 /* ------------------------------------------------------------------------------------------------------ */
 
-/* Least squares min ||A y - b|| by Householder QR, A is rows x 6 row-major and is overwritten; b too.
- * (Ceres: dense_qr_solver.cc -> Eigen householderQr().solve()).  Returns 0 on success. */
-static int householder_ls6(double* A, double* b, int64_t rows, double y[6]) {
+/* In-place Householder triangularisation of the rows x 6 row-major A (rows >= 6) and of the rhs b: on exit the
+ * top 6 x 6 of A is R and b[0..5] is (Q^T b)[0..5].  Returns non-zero for a zero column. */
+static int hh_factor6(double* A, double* b, int64_t rows) {
   const int n = 6;
   for (int k = 0; k < n; ++k) {
     double nrm2 = 0.0;
@@ -398,31 +398,64 @@ static int householder_ls6(double* A, double* b, int64_t rows, double y[6]) {
     if (!(nrm > 0.0)) return 1;
     const double akk = A[(int64_t)k * n + k];
     const double alpha = akk > 0.0 ? -nrm : nrm;
-    /* v = x - alpha e1, stored in column k from row k; beta = 2/(v^T v) */
+    /* v = x - alpha e1 (stored in column k below the diagonal, v0 separately); beta = 2 / v^T v */
     const double v0 = akk - alpha;
     const double vtv = nrm2 - akk * akk + v0 * v0;
-    if (!(vtv > 0.0)) { A[(int64_t)k * n + k] = alpha; continue; }
-    const double beta = 2.0 / vtv;
-    for (int j = k + 1; j < n; ++j) {
-      double s = v0 * A[(int64_t)k * n + j];
-      for (int64_t i = k + 1; i < rows; ++i) s += A[i * n + k] * A[i * n + j];
-      s *= beta;
-      A[(int64_t)k * n + j] -= s * v0;
-      for (int64_t i = k + 1; i < rows; ++i) A[i * n + j] -= s * A[i * n + k];
-    }
-    {
-      double s = v0 * b[k];
-      for (int64_t i = k + 1; i < rows; ++i) s += A[i * n + k] * b[i];
-      s *= beta;
-      b[k] -= s * v0;
-      for (int64_t i = k + 1; i < rows; ++i) b[i] -= s * A[i * n + k];
+    if (vtv > 0.0) {
+      const double beta = 2.0 / vtv;
+      /* one pass for all dot products v^T [A(:,k+1..5) b], one pass for the rank-1 update */
+      double s[7];
+      for (int j = k + 1; j < n; ++j) s[j] = v0 * A[(int64_t)k * n + j];
+      s[6] = v0 * b[k];
+      for (int64_t i = k + 1; i < rows; ++i) {
+        const double vi = A[i * n + k];
+        for (int j = k + 1; j < n; ++j) s[j] += vi * A[i * n + j];
+        s[6] += vi * b[i];
+      }
+      for (int j = k + 1; j < n; ++j) { s[j] *= beta; A[(int64_t)k * n + j] -= s[j] * v0; }
+      s[6] *= beta;
+      b[k] -= s[6] * v0;
+      for (int64_t i = k + 1; i < rows; ++i) {
+        const double vi = A[i * n + k];
+        for (int j = k + 1; j < n; ++j) A[i * n + j] -= s[j] * vi;
+        b[i] -= s[6] * vi;
+      }
     }
     A[(int64_t)k * n + k] = alpha;
   }
+  return 0;
+}
+
+/* Least squares min ||A y - b|| by Householder QR of the rows x 6 row-major A (Ceres: dense_qr_solver.cc ->
+ * Eigen householderQr().solve()).  A and b are overwritten.  Tall matrices are processed as a sequence of
+ * cache-resident row blocks stacked under the running 6 x 6 triangular factor (a Householder QR of the same matrix,
+ * organised so that it streams A once -- this keeps the timed CPU baseline honest).  Returns 0 on success. */
+#define HH_BLOCK 2048
+static int householder_ls6(double* A, double* b, int64_t rows, double y[6]) {
+  const int n = 6;
+  double* R = A;
+  double* qtb = b;
+  double W[(HH_BLOCK + 6) * 6], wb[HH_BLOCK + 6];
+  if (rows > HH_BLOCK + 6) {
+    int have = 0;
+    for (int64_t r0 = 0; r0 < rows; r0 += HH_BLOCK) {
+      const int64_t nb = (rows - r0 < HH_BLOCK) ? rows - r0 : HH_BLOCK;
+      memcpy(W + have * n, A + r0 * n, sizeof(double) * (size_t)nb * n);
+      memcpy(wb + have, b + r0, sizeof(double) * (size_t)nb);
+      if (hh_factor6(W, wb, have + nb)) return 1;
+      for (int i = 1; i < n; ++i)
+        for (int j = 0; j < i; ++j) W[i * n + j] = 0.0; /* keep only R for the next stack */
+      have = n;
+    }
+    R = W;
+    qtb = wb;
+  } else {
+    if (hh_factor6(A, b, rows)) return 1;
+  }
   for (int k = n - 1; k >= 0; --k) {
-    double s = b[k];
-    for (int j = k + 1; j < n; ++j) s -= A[(int64_t)k * n + j] * y[j];
-    y[k] = s / A[(int64_t)k * n + k];
+    double sacc = qtb[k];
+    for (int j = k + 1; j < n; ++j) sacc -= R[k * n + j] * y[j];
+    y[k] = sacc / R[k * n + k];
   }
   return 0;
 }
