@@ -48,12 +48,12 @@ UNIT = "residual evals/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
     ap.add_argument("--beams", type=int, default=BEAMS)
-    ap.add_argument("--kernel-launches", type=int, default=40, help="timed launches of the sweep kernel for the roofline")
+    ap.add_argument("--kernel-launches", type=int, default=100, help="timed launches of the sweep kernel for the roofline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -171,17 +171,20 @@ def run_reference(args):
     cores = max(rates, key=rates.get)
     for _ in range(max(0, args.warmup - len(rates))):
         time_cpu_solve(p, cores, 0)
-    t_tot, ev_tot, iters = 0.0, 0, 0
+    t_tot, ev_tot, iters, steps_done = 0.0, 0, 0, 0
     for _ in range(args.steps):
         dt, ev, iters = time_cpu_solve(p, cores, 0)
         t_tot += dt
         ev_tot += ev
+        steps_done += 1
+        if t_tot > 120.0:  # keep the whole run within a few minutes whatever --steps says
+            break
     value = ev_tot / t_tot
     sample = (f"each step = one full LM solve on the first {n} of {args.frames} frames x {args.beams} points "
               f"({n * args.beams} residuals, {iters} iterations); Ceres-shaped oracle port, evaluation on {cores} threads")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / steps_done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[1]: {args.frames} frames x {args.beams} points per GPU, sigma={SIGMA} m, "
                                f"identity start, full LM solve (bounded CPU sample: {n} frames)"},
@@ -267,7 +270,6 @@ def run_ours(args):
     prob.bench_eval(x, 5, flush_l2=True)
     k_ms = prob.bench_eval(x, args.kernel_launches, flush_l2=True)
     launches += args.kernel_launches
-    clocks = sampler.stop() if rank == 0 else None
     k_mean = float(np.mean(k_ms))
     alg_bytes = prob.algorithmic_bytes()
     peaks, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -303,7 +305,7 @@ def run_ours(args):
             _, ss, _ = q.solve(X0, opt)
         return ss
 
-    e2e_steps = max(3, min(args.steps, 5))
+    e2e_steps = max(3, min(args.steps, 10))
     e2e_sweeps = 0
     e2e_step()  # warm-up
     barrier()
@@ -321,6 +323,7 @@ def run_ours(args):
                    "destroy; wall clock, max over ranks"}
     pin_pts.free()
     pin_fp.free()
+    clocks = sampler.stop() if rank == 0 else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

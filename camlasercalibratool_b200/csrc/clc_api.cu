@@ -260,11 +260,11 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
   a.use_edges = edges ? 1 : 0;
   const clc::ProblemView v = make_view(p);
   if (mode == clc::kModeClosedForm) {
-    clc::clc_sweep_kernel<false, clc::kModeClosedForm><<<p->grid, clc::kThreads, 0, p->stream>>>(v, a);
+    clc::clc_sweep_kernel<false, clc::kModeClosedForm><<<p->grid, clc::kThreads, clc::kDynSmemBytes, p->stream>>>(v, a);
   } else if (loss) {
-    clc::clc_sweep_kernel<true, clc::kModeLM><<<p->grid, clc::kThreads, 0, p->stream>>>(v, a);
+    clc::clc_sweep_kernel<true, clc::kModeLM><<<p->grid, clc::kThreads, clc::kDynSmemBytes, p->stream>>>(v, a);
   } else {
-    clc::clc_sweep_kernel<false, clc::kModeLM><<<p->grid, clc::kThreads, 0, p->stream>>>(v, a);
+    clc::clc_sweep_kernel<false, clc::kModeLM><<<p->grid, clc::kThreads, clc::kDynSmemBytes, p->stream>>>(v, a);
   }
   CLC_LAUNCH_CHECK();
   return CLC_OK;
@@ -286,11 +286,14 @@ int finish_create(clc_problem* p) {
   }
   // persistent grid: SM count x resident blocks per SM (the smallest occupancy of the instantiations used)
   int occ = 0, occ_min = 1 << 30;
-  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<true, clc::kModeLM>, clc::kThreads, 0));
+  CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<true, clc::kModeLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
+  CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<false, clc::kModeLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
+  CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<false, clc::kModeClosedForm>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
+  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<true, clc::kModeLM>, clc::kThreads, clc::kDynSmemBytes));
   occ_min = std::min(occ_min, occ);
-  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeLM>, clc::kThreads, 0));
+  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeLM>, clc::kThreads, clc::kDynSmemBytes));
   occ_min = std::min(occ_min, occ);
-  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeClosedForm>, clc::kThreads, 0));
+  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeClosedForm>, clc::kThreads, clc::kDynSmemBytes));
   occ_min = std::min(occ_min, occ);
   int blocks_per_sm = std::max(1, occ_min);
   if (const char* env = std::getenv("CLC_BLOCKS_PER_SM")) {
@@ -299,7 +302,7 @@ int finish_create(clc_problem* p) {
   }
   p->grid = p->num_sms * blocks_per_sm;
   const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
-  p->per_warp = std::max<int64_t>(clc::kGroup, round_up((p->n_points + n_warps - 1) / n_warps, clc::kGroup));
+  p->per_warp = std::max<int64_t>(clc::kChunk, round_up((p->n_points + n_warps - 1) / n_warps, clc::kChunk));
   CLC_CUDA(cudaMalloc(&p->warp_first_frame, sizeof(int) * n_warps));
   {
     const int blocks = (int)((n_warps + threads - 1) / threads);
@@ -340,7 +343,7 @@ int init_device(clc_problem* p, int device) {
 }
 
 int alloc_points(clc_problem* p) {
-  p->n_points_padded = round_up(p->n_points, clc::kGroup) + 2 * clc::kGroup;
+  p->n_points_padded = round_up(p->n_points, clc::kChunk) + clc::kChunk;
   const size_t bytes = sizeof(double) * (size_t)p->n_points_padded;
   CLC_CUDA(cudaMalloc(&p->x, bytes));
   CLC_CUDA(cudaMalloc(&p->y, bytes));

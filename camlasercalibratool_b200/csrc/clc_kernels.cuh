@@ -17,14 +17,17 @@ namespace clc {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTileStride = 13;       // doubles per tile row: 10 moments, product, exponent, frame id
-constexpr int kGroup = 64;            // points per warp iteration (2 per lane, one LDG.128 per array)
+constexpr int kChunk = 128;           // points per pipeline stage and coordinate array (one 1 KiB bulk copy each)
+constexpr int kStages = 3;            // bulk-copy stages in flight per warp (3 x 3 KiB)
 constexpr int kMaxOut = 54;           // closed-form mode: 45 + 9
+constexpr int kRingDoublesPerWarp = kStages * 3 * kChunk;
+constexpr int kDynSmemBytes = kWarps * kRingDoublesPerWarp * 8 + kWarps * kStages * 8;
 
 enum SweepMode { kModeLM = 0, kModeClosedForm = 1 };
 
 // Device-resident problem (read-only for the sweeps).
 struct ProblemView {
-  const double* x;            // SoA coordinates, zero padded to a multiple of kGroup (+ kGroup)
+  const double* x;            // SoA coordinates, zero padded to a multiple of kChunk (+ kChunk)
   const double* y;
   const double* z;
   const double* plane;        // [n_frames*4]   n, d in the camera frame
@@ -35,7 +38,7 @@ struct ProblemView {
   int64_t n_frames;
   int64_t n_points;
   int64_t n_edges;            // 2 * n_frames or 0
-  int64_t per_warp;           // points per warp (multiple of kGroup)
+  int64_t per_warp;           // points per warp (multiple of kChunk)
   double inv_a2;              // 1 / cauchy_a^2
   double a2;                  // cauchy_a^2
 };
@@ -53,11 +56,32 @@ struct SweepArgs {
 
 // ---- small device helpers ---------------------------------------------------------------------------------
 
-__device__ __forceinline__ double2 ldg_stream2(const double* p) {
-  // 128-bit read-only load; data is touched once per sweep -> do not pollute L1
-  double2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
-  return v;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); completion is signalled on `bar` in bytes
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // 1/a for a normal, positive a: MUFU.RCP64H seed (2^-23 relative) + two Newton steps (-> ~1 ulp).
@@ -139,18 +163,22 @@ __device__ __forceinline__ void renormalise(Moments& a) {
 
 // ---- K1: the fused sweep -------------------------------------------------------------------------------------
 //
-// Work decomposition: the P points are cut into equal contiguous ranges, one per warp of a grid that fills the
-// machine exactly once (persistent, SM-count x occupancy blocks).  A warp walks its range frame piece by frame
-// piece; within a piece each lane streams 2 points per 128-bit load triple and keeps 10 weighted moments plus
-// the running cost product in registers.  At the end of a piece the lanes' moments are summed by warp shuffles
-// and parked in a shared-memory tile; every 32 pieces (and at the end) the tile is expanded -- one piece per
-// lane -- into the 28 normal-equation sums, which are shuffle-reduced and added to the warp's accumulator in
-// shared memory.  Block partials go to global memory; the last block to finish (ticket) adds them in a fixed
-// order, so the result is bit-reproducible from run to run, and optionally runs the LM update.
+// Work decomposition: the P points are cut into equal contiguous ranges (a multiple of 128 points), one per warp of
+// a grid that fills the machine exactly once (persistent: SM count x resident blocks).  Every warp owns a private
+// 3-stage ring in shared memory that the TMA engine fills with 1 KiB bulk copies (cp.async.bulk, one per coordinate
+// array and stage; completion on an mbarrier), so ~9 KiB per warp / ~144 KiB per SM are in flight regardless of
+// register pressure and independent of the frame bookkeeping.  The warp consumes a stage with conflict-free 128-bit
+// shared loads (4 points per lane), walks the frame pieces that overlap the stage, and keeps 10 weighted moments
+// plus the running cost product per lane in registers.  When a frame ends, the lanes' moments are summed by warp
+// shuffles and parked in a shared-memory tile; every 32 pieces (and at the end) the tile is expanded -- one piece
+// per lane -- into the 28 normal-equation sums, which are shuffle-reduced into the warp's accumulator.  Block
+// partials go to global memory; the last block to finish (ticket) adds them in a fixed order, so the result is
+// bit-reproducible from run to run, and optionally runs the LM update.
 template <bool LOSS, int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
 clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   constexpr int NOUT = (MODE == kModeLM) ? kNumSums : kMaxOut;
+  extern __shared__ __align__(128) unsigned char s_dyn[];
   __shared__ double s_tile[kWarps][32 * kTileStride];
   __shared__ double s_acc[kWarps][NOUT];
   __shared__ double s_red[kWarps][32];
@@ -161,6 +189,34 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int64_t gwarp = (int64_t)blockIdx.x * kWarps + warp;
+
+  // ---- this warp's range and ring; start the copies before anything else (they do not depend on the pose) ----
+  const int64_t P = pv.n_points;
+  int64_t p0 = gwarp * pv.per_warp;
+  if (p0 > P) p0 = P;
+  int64_t p1 = p0 + pv.per_warp;
+  if (p1 > P) p1 = P;
+  const int n_chunks = (int)((p1 - p0 + kChunk - 1) / kChunk);
+  double* ring = reinterpret_cast<double*>(s_dyn) + warp * kRingDoublesPerWarp;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (size_t)kWarps * kRingDoublesPerWarp * 8) + warp * kStages;
+
+  auto issue_chunk = [&](int c) {  // lane 0 only
+    const int st = c % kStages;
+    double* dst = ring + st * 3 * kChunk;
+    const int64_t src = p0 + (int64_t)c * kChunk;  // multiple of 128 points -> 1 KiB aligned
+    mbar_expect_tx(bars + st, 3 * kChunk * 8);
+    bulk_g2s(dst, pv.x + src, kChunk * 8, bars + st);
+    bulk_g2s(dst + kChunk, pv.y + src, kChunk * 8, bars + st);
+    bulk_g2s(dst + 2 * kChunk, pv.z + src, kChunk * 8, bars + st);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) mbar_init(bars + st, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int c = 0; c < kStages && c < n_chunks; ++c) issue_chunk(c);
+  }
+  __syncwarp();
 
   for (int k = lane; k < NOUT; k += 32) s_acc[warp][k] = 0.0;
 
@@ -207,46 +263,40 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     n_tile = 0;
   };
 
-  // ---- main stream over this warp's point range ----
-  const int64_t P = pv.n_points;
-  int64_t p = gwarp * pv.per_warp;
-  if (p > P) p = P;
-  int64_t p_end = p + pv.per_warp;
-  if (p_end > P) p_end = P;
-  if (p < p_end) {
+  // ---- main stream ----
+  if (n_chunks > 0) {
     int64_t f = pv.warp_first_frame[gwarp];
-    while (p < p_end) {
-      const int64_t f_end = pv.offsets[f + 1];
-      if (f_end <= p) { ++f; continue; }
-      const int64_t pe = f_end < p_end ? f_end : p_end;
-      // frame constants (every lane, redundantly)
-      double m0, m1, m2, c;
-      {
-        double plane[4], m[3];
+    int64_t f_end = pv.offsets[f + 1];
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, c = 0.0;
+    // frame constants (every lane, redundantly); the next frame's plane and end offset are prefetched one piece
+    // ahead so that a frame change does not stall the stream on a global-memory round trip
+    double nx_plane[4] = {0.0, 0.0, 0.0, 0.0};
+    int64_t nx_end = 0;
+    auto prefetch_next = [&]() {
+      if (f + 1 < pv.n_frames) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) plane[k] = pv.plane[f * 4 + k];
-        frame_consts(pc, plane, m, &c);
-        m0 = m[0]; m1 = m[1]; m2 = m[2];
+        for (int k = 0; k < 4; ++k) nx_plane[k] = pv.plane[(f + 1) * 4 + k];
+        nx_end = pv.offsets[f + 2];
       }
-      Moments a;
-      moments_clear<LOSS>(a);
-      // lanes take points (k, k+1); k is even so the 128-bit loads are aligned
-      int64_t k = (p & ~(int64_t)1) + 2 * lane;
-      for (; k + kGroup < pe; k += 2 * kGroup) {
-        // two groups in flight: 6 independent LDG.128 per lane
-        const double2 X0 = ldg_stream2(pv.x + k), Y0 = ldg_stream2(pv.y + k), Z0 = ldg_stream2(pv.z + k);
-        const double2 X1 = ldg_stream2(pv.x + k + kGroup), Y1 = ldg_stream2(pv.y + k + kGroup),
-                      Z1 = ldg_stream2(pv.z + k + kGroup);
-        process2<LOSS, MODE == kModeLM>(a, X0, Y0, Z0, k >= p, true, m0, m1, m2, c, pv.inv_a2);
-        process2<LOSS, MODE == kModeLM>(a, X1, Y1, Z1, true, k + kGroup + 1 < pe, m0, m1, m2, c, pv.inv_a2);
-        if (LOSS) renormalise(a);
-      }
-      if (k < pe) {
-        const double2 X0 = ldg_stream2(pv.x + k), Y0 = ldg_stream2(pv.y + k), Z0 = ldg_stream2(pv.z + k);
-        process2<LOSS, MODE == kModeLM>(a, X0, Y0, Z0, k >= p, k + 1 < pe, m0, m1, m2, c, pv.inv_a2);
-        if (LOSS) renormalise(a);
-      }
-      // ---- piece reduction over the 32 lanes ----
+    };
+    auto set_frame_consts = [&](const double* plane) {
+      double m[3];
+      frame_consts(pc, plane, m, &c);
+      m0 = m[0]; m1 = m[1]; m2 = m[2];
+    };
+    {
+      double plane[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) plane[k] = pv.plane[f * 4 + k];
+      set_frame_consts(plane);
+      prefetch_next();
+    }
+    Moments a;
+    moments_clear<LOSS>(a);
+    bool open = false;  // the current piece has accumulated points
+
+    // sums the lanes' moments of the finished piece and parks them in the tile
+    auto park_piece = [&]() {
       const double r0 = warp_sum(a.S0), r1 = warp_sum(a.Sx), r2 = warp_sum(a.Sy), r3 = warp_sum(a.Sz);
       const double r4 = warp_sum(a.Sxx), r5 = warp_sum(a.Sxy), r6 = warp_sum(a.Sxz);
       const double r7 = warp_sum(a.Syy), r8 = warp_sum(a.Syz), r9 = warp_sum(a.Szz);
@@ -269,9 +319,68 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
       }
       ++n_tile;
       if (n_tile == 32) flush_tile();
-      p = pe;
-      if (pe == f_end) ++f;
+      moments_clear<LOSS>(a);
+      open = false;
+    };
+
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int st = ch % kStages;
+      const int64_t cb = p0 + (int64_t)ch * kChunk;
+      const int64_t ce = (cb + kChunk < p1) ? cb + kChunk : p1;
+      mbar_wait(bars + st, (uint32_t)(ch / kStages) & 1u);
+      const double* sx = ring + st * 3 * kChunk;
+      // this lane's 4 points of the stage: local indices 2*lane, 2*lane+1, 64+2*lane, 65+2*lane
+      const double2 X0 = *reinterpret_cast<const double2*>(sx + 2 * lane);
+      const double2 Y0 = *reinterpret_cast<const double2*>(sx + kChunk + 2 * lane);
+      const double2 Z0 = *reinterpret_cast<const double2*>(sx + 2 * kChunk + 2 * lane);
+      const double2 X1 = *reinterpret_cast<const double2*>(sx + 64 + 2 * lane);
+      const double2 Y1 = *reinterpret_cast<const double2*>(sx + kChunk + 64 + 2 * lane);
+      const double2 Z1 = *reinterpret_cast<const double2*>(sx + 2 * kChunk + 64 + 2 * lane);
+      int64_t q = cb;
+      while (q < ce) {
+        while (f_end <= q) {  // next non-empty frame
+          ++f;
+          if (nx_end > q) {   // the prefetched frame is the one (the common case)
+            f_end = nx_end;
+            set_frame_consts(nx_plane);
+          } else {
+            f_end = pv.offsets[f + 1];
+            if (f_end > q) {
+              double plane[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) plane[k] = pv.plane[f * 4 + k];
+              set_frame_consts(plane);
+            }
+          }
+          if (f_end > q) prefetch_next();
+          else nx_end = 0;
+        }
+        const int64_t hi = f_end < ce ? f_end : ce;
+        if (q == cb && hi == cb + kChunk) {
+          // the whole stage belongs to one frame: no masks
+          process2<LOSS, MODE == kModeLM>(a, X0, Y0, Z0, true, true, m0, m1, m2, c, pv.inv_a2);
+          process2<LOSS, MODE == kModeLM>(a, X1, Y1, Z1, true, true, m0, m1, m2, c, pv.inv_a2);
+        } else {
+          const int64_t i0 = cb + 2 * lane, i2 = i0 + 64;
+          process2<LOSS, MODE == kModeLM>(a, X0, Y0, Z0, i0 >= q && i0 < hi, i0 + 1 >= q && i0 + 1 < hi, m0, m1, m2, c,
+                                          pv.inv_a2);
+          process2<LOSS, MODE == kModeLM>(a, X1, Y1, Z1, i2 >= q && i2 < hi, i2 + 1 >= q && i2 + 1 < hi, m0, m1, m2, c,
+                                          pv.inv_a2);
+        }
+        if (LOSS) renormalise(a);
+        open = true;
+        q = hi;
+        if (hi == f_end) park_piece();
+      }
+      // every lane has consumed its registers' worth of the stage (data dependence), so the slot can be handed
+      // back to the TMA engine: two more stages stay in flight meanwhile
+      __syncwarp();
+      if (lane == 0 && ch + kStages < n_chunks) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_chunk(ch + kStages);
+      }
     }
+    if (open) park_piece();  // the last frame continues in the next warp's range
   }
   flush_tile();
 

@@ -126,7 +126,7 @@ def harness(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("harness") / "libclc_host_harness.so")
     src = os.path.join(ROOT, "tests", "host_harness.cpp")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.check_call([cxx, "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src])
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-shared", "-fPIC", "-o", out, src])
     return Harness(out)
 
 
