@@ -288,7 +288,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks, "unit": "GB/s", "frac": achieved / peaks,
                 "traffic": traffic, "kernel": "clc_sweep_kernel<LOSS,LM>", "kernel_ms_mean": k_mean,
                 "kernel_ms_min": float(np.min(k_ms)), "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "residuals_per_s_kernel": n_points / (k_mean * 1e-3), "l2": "flushed (256 MiB write) between launches"}
+                "residuals_per_s_kernel": n_points / (k_mean * 1e-3), "l2": "flushed between launches (256 MiB written, then read back so that no dirty lines are left)"}
 
     # ---- end-to-end leg: host (pinned) buffers -> create (H2D + layout) -> solve -> D2H result -> destroy ----
     d = prob.download()

@@ -37,7 +37,9 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+    extra = os.environ.get("CLC_NVCC_EXTRA", "").split()  # experiment knobs, e.g. -DCLC_THREADS=512 -DCLC_BLOCKS_PER_SM=1
+    out = os.environ.get("CLC_LIB_OUT", LIB_PATH)
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -46,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

@@ -145,8 +145,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.is_stale():
+    path = os.environ.get("CLC_LIB_PATH", _build.LIB_PATH)  # CLC_LIB_PATH: load an experimental build variant
+    if path == _build.LIB_PATH and _build.is_stale():
         try:
             _build.build()
         except Exception as exc:  # no nvcc on this box: use the prebuilt file if there is one

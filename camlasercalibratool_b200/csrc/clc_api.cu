@@ -211,6 +211,7 @@ struct clc_problem {
   clc::LmState* lm = nullptr;
   double* flush_buf = nullptr;
   int64_t flush_n = 0;
+  unsigned long long* timing = nullptr;  // profiling hook (clc_debug_sweep_timing)
   // pinned host mirrors
   double* h_sums = nullptr;
   int* h_done = nullptr;
@@ -258,6 +259,7 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
   a.lm = d_lm;
   a.use_loss = loss ? 1 : 0;
   a.use_edges = edges ? 1 : 0;
+  a.timing = p->timing;
   const clc::ProblemView v = make_view(p);
   if (mode == clc::kModeClosedForm) {
     clc::clc_sweep_kernel<false, clc::kModeClosedForm><<<p->grid, clc::kThreads, clc::kDynSmemBytes, p->stream>>>(v, a);
@@ -295,7 +297,7 @@ int finish_create(clc_problem* p) {
   occ_min = std::min(occ_min, occ);
   CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeClosedForm>, clc::kThreads, clc::kDynSmemBytes));
   occ_min = std::min(occ_min, occ);
-  int blocks_per_sm = std::max(1, occ_min);
+  int blocks_per_sm = std::max(1, std::min(occ_min, clc::kBlocksPerSM));
   if (const char* env = std::getenv("CLC_BLOCKS_PER_SM")) {
     const int v = std::atoi(env);
     if (v >= 1) blocks_per_sm = std::min(v, std::max(1, occ_min));
@@ -856,6 +858,8 @@ int clc_bench_eval(clc_problem* p, const double pose7[7], int n, int flush_l2, f
     if (flush_l2) {
       clc::clc_flush_kernel<<<p->num_sms * 4, 256, 0, p->stream>>>(p->flush_buf, p->flush_n, (double)i);
       CLC_LAUNCH_CHECK();
+      clc::clc_flush_read_kernel<<<p->num_sms * 4, 256, 0, p->stream>>>(p->flush_buf, p->flush_n, p->flush_buf);
+      CLC_LAUNCH_CHECK();
     }
     CLC_CUDA(cudaEventRecord(ev[2 * i], p->stream));
     rc = launch_sweep(p, clc::kModeLM, loss, edges, p->pose, nullptr, nullptr);
@@ -865,6 +869,43 @@ int clc_bench_eval(clc_problem* p, const double pose7[7], int n, int flush_l2, f
   CLC_CUDA(cudaStreamSynchronize(p->stream));
   for (int i = 0; i < n; ++i) CLC_CUDA(cudaEventElapsedTime(&ms_each[i], ev[2 * i], ev[2 * i + 1]));
   for (auto& e : ev) cudaEventDestroy(e);
+  return CLC_OK;
+}
+
+// Profiling hook (not part of the reference-facing surface): one sweep with per-block globaltimer stamps.
+// stamps[grid*8]: 0 block start, 1 stream done, 2 tile flushed, 3 block partial written, 4 (last block) final sums,
+// 5 (last block) after the LM update.  with_lm != 0 runs the fused LM update of a fresh LM state at pose7.
+int clc_debug_sweep_timing(clc_problem* p, const double pose7[7], int with_lm, int flush_l2, unsigned long long* stamps,
+                           int* grid_out) {
+  if (!p || !pose7 || !stamps) return fail(CLC_ERR_INVALID, "bad timing arguments");
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  if (grid_out) *grid_out = p->grid;
+  const size_t bytes = sizeof(unsigned long long) * 8 * (size_t)p->grid;
+  CLC_CUDA(cudaMalloc(&p->timing, bytes));
+  CLC_CUDA(cudaMemsetAsync(p->timing, 0, bytes, p->stream));
+  if (flush_l2) {
+    if (!p->flush_buf) {
+      p->flush_n = ((int64_t)256 << 20) / sizeof(double);
+      CLC_CUDA(cudaMalloc(&p->flush_buf, sizeof(double) * p->flush_n));
+    }
+    clc::clc_flush_kernel<<<p->num_sms * 4, 256, 0, p->stream>>>(p->flush_buf, p->flush_n, 1.0);
+    CLC_LAUNCH_CHECK();
+    clc::clc_flush_read_kernel<<<p->num_sms * 4, 256, 0, p->stream>>>(p->flush_buf, p->flush_n, p->flush_buf);
+    CLC_LAUNCH_CHECK();
+  }
+  clc_lm_options opt;
+  clc_lm_default_options(&opt);
+  clc::lm_init(p->h_lm, pose7, opt);
+  CLC_CUDA(cudaMemcpyAsync(p->lm, p->h_lm, sizeof(clc::LmState), cudaMemcpyHostToDevice, p->stream));
+  CLC_CUDA(cudaMemcpyAsync(p->pose, pose7, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
+  rc = launch_sweep(p, clc::kModeLM, p->use_loss != 0, p->n_edges > 0, p->pose, nullptr, with_lm ? p->lm : nullptr);
+  cudaError_t e = cudaMemcpyAsync(stamps, p->timing, bytes, cudaMemcpyDeviceToHost, p->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+  cudaFree(p->timing);
+  p->timing = nullptr;
+  if (rc != CLC_OK) return rc;
+  if (e != cudaSuccess) return fail(CLC_ERR_CUDA, cudaGetErrorString(e));
   return CLC_OK;
 }
 

@@ -257,15 +257,12 @@ CLC_HD int tri(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }  //
 
 // Cholesky solve of the SPD 6x6 system A y = b (A full row-major).  false if not positive definite.
 CLC_HD bool chol6_solve(const double* A, const double* b, double* y) {
-  // fully unrolled so that L, z live in registers on the device (this runs on one thread between two sweeps)
+  // deliberately compact (rolled loops): this runs once per sweep on one thread from a cold instruction cache
   double L[36];
   bool ok = true;
-#pragma unroll
   for (int i = 0; i < 6; ++i) {
-#pragma unroll
     for (int j = 0; j <= i; ++j) {
       double s = A[i * 6 + j];
-#pragma unroll
       for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
       if (i == j) {
         ok = ok && (s > 0.0);
@@ -277,17 +274,13 @@ CLC_HD bool chol6_solve(const double* A, const double* b, double* y) {
   }
   if (!ok) return false;
   double z[6];
-#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
-#pragma unroll
     for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * z[k];
     z[i] = s / L[i * 6 + i];
   }
-#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
-#pragma unroll
     for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * y[k];
     y[i] = s / L[i * 6 + i];
   }
