@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -182,6 +183,35 @@ int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
+// ---- pinned host mirrors: pooled process-wide (cudaMallocHost costs milliseconds) ---------------------------------
+struct PinnedBlock {
+  clc::LmState lm;
+  double sums[clc::kMaxOut];
+  int done;
+};
+namespace {
+std::mutex g_pinned_mutex;
+std::vector<PinnedBlock*> g_pinned_free;
+PinnedBlock* pinned_acquire() {
+  {
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    if (!g_pinned_free.empty()) {
+      PinnedBlock* b = g_pinned_free.back();
+      g_pinned_free.pop_back();
+      return b;
+    }
+  }
+  PinnedBlock* b = nullptr;
+  if (cudaMallocHost(&b, sizeof(PinnedBlock)) != cudaSuccess) return nullptr;
+  return b;
+}
+void pinned_release(PinnedBlock* b) {
+  if (!b) return;
+  std::lock_guard<std::mutex> lock(g_pinned_mutex);
+  g_pinned_free.push_back(b);
+}
+}  // namespace
+
 // ---- the communicator and problem objects ------------------------------------------------------------------------
 struct clc_comm {
   ncclComm_t comm = nullptr;
@@ -212,7 +242,8 @@ struct clc_problem {
   double* flush_buf = nullptr;
   int64_t flush_n = 0;
   unsigned long long* timing = nullptr;  // profiling hook (clc_debug_sweep_timing)
-  // pinned host mirrors
+  // pinned host mirrors (views into one pooled block)
+  PinnedBlock* pinned = nullptr;
   double* h_sums = nullptr;
   int* h_done = nullptr;
   clc::LmState* h_lm = nullptr;
@@ -305,23 +336,25 @@ int finish_create(clc_problem* p) {
   p->grid = p->num_sms * blocks_per_sm;
   const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
   p->per_warp = std::max<int64_t>(clc::kChunk, round_up((p->n_points + n_warps - 1) / n_warps, clc::kChunk));
-  CLC_CUDA(cudaMalloc(&p->warp_first_frame, sizeof(int) * n_warps));
+  CLC_CUDA(cudaMallocAsync(&p->warp_first_frame, sizeof(int) * n_warps, p->stream));
   {
     const int blocks = (int)((n_warps + threads - 1) / threads);
     clc::clc_warp_table_kernel<<<blocks, threads, 0, p->stream>>>(p->offsets, p->n_frames, p->n_points, p->per_warp,
                                                                   n_warps, p->warp_first_frame);
     CLC_LAUNCH_CHECK();
   }
-  CLC_CUDA(cudaMalloc(&p->partials, sizeof(double) * (size_t)p->grid * clc::kMaxOut));
-  CLC_CUDA(cudaMalloc(&p->sums, sizeof(double) * clc::kMaxOut));
-  CLC_CUDA(cudaMalloc(&p->pose, sizeof(double) * 8));
-  CLC_CUDA(cudaMalloc(&p->ticket, sizeof(unsigned int)));
-  CLC_CUDA(cudaMalloc(&p->lm, sizeof(clc::LmState)));
+  CLC_CUDA(cudaMallocAsync(&p->partials, sizeof(double) * (size_t)p->grid * clc::kMaxOut, p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->sums, sizeof(double) * clc::kMaxOut, p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->pose, sizeof(double) * 8, p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->ticket, sizeof(unsigned int), p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->lm, sizeof(clc::LmState), p->stream));
   CLC_CUDA(cudaMemsetAsync(p->ticket, 0, sizeof(unsigned int), p->stream));
   CLC_CUDA(cudaMemsetAsync(p->sums, 0, sizeof(double) * clc::kMaxOut, p->stream));
-  CLC_CUDA(cudaMallocHost(&p->h_sums, sizeof(double) * clc::kMaxOut));
-  CLC_CUDA(cudaMallocHost(&p->h_done, sizeof(int)));
-  CLC_CUDA(cudaMallocHost(&p->h_lm, sizeof(clc::LmState)));
+  p->pinned = pinned_acquire();
+  if (!p->pinned) return fail(CLC_ERR_CUDA, "cudaMallocHost failed");
+  p->h_sums = p->pinned->sums;
+  p->h_done = &p->pinned->done;
+  p->h_lm = &p->pinned->lm;
   CLC_CUDA(cudaStreamSynchronize(p->stream));
   return CLC_OK;
 }
@@ -340,6 +373,13 @@ int init_device(clc_problem* p, int device) {
     return fail(CLC_ERR_CUDA, std::string("libclc_b200 is built for sm_100a only; device is sm_") +
                                   std::to_string(prop.major) + std::to_string(prop.minor));
   p->num_sms = prop.multiProcessorCount;
+  {
+    // keep freed device memory in the pool instead of returning it to the driver at every synchronisation
+    cudaMemPool_t pool;
+    CLC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t threshold = UINT64_MAX;
+    CLC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  }
   CLC_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   return CLC_OK;
 }
@@ -347,9 +387,9 @@ int init_device(clc_problem* p, int device) {
 int alloc_points(clc_problem* p) {
   p->n_points_padded = round_up(p->n_points, clc::kChunk) + clc::kChunk;
   const size_t bytes = sizeof(double) * (size_t)p->n_points_padded;
-  CLC_CUDA(cudaMalloc(&p->x, bytes));
-  CLC_CUDA(cudaMalloc(&p->y, bytes));
-  CLC_CUDA(cudaMalloc(&p->z, bytes));
+  CLC_CUDA(cudaMallocAsync(&p->x, bytes, p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->y, bytes, p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->z, bytes, p->stream));
   // zero the padding (finite values are required beyond the last point)
   const int64_t tail = p->n_points_padded - p->n_points;
   CLC_CUDA(cudaMemsetAsync(p->x + p->n_points, 0, sizeof(double) * tail, p->stream));
@@ -410,12 +450,15 @@ int clc_problem_destroy(clc_problem* p) {
   if (!p) return CLC_OK;
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
-  cudaFree(p->x); cudaFree(p->y); cudaFree(p->z);
-  cudaFree(p->frame_pose); cudaFree(p->plane); cudaFree(p->offsets); cudaFree(p->warp_first_frame);
-  cudaFree(p->edge_plane); cudaFree(p->edge_pt); cudaFree(p->partials); cudaFree(p->sums); cudaFree(p->pose);
-  cudaFree(p->ticket); cudaFree(p->lm); cudaFree(p->flush_buf);
-  cudaFreeHost(p->h_sums); cudaFreeHost(p->h_done); cudaFreeHost(p->h_lm);
-  if (p->stream) cudaStreamDestroy(p->stream);
+  if (p->stream) {
+    void* bufs[] = {p->x, p->y, p->z, p->frame_pose, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
+                    p->partials, p->sums, p->pose, p->ticket, p->lm, p->flush_buf};
+    for (void* b : bufs)
+      if (b) cudaFreeAsync(b, p->stream);  // back to the device's memory pool: re-creating a problem is cheap
+    cudaStreamSynchronize(p->stream);
+    cudaStreamDestroy(p->stream);
+  }
+  pinned_release(p->pinned);
   delete p;
   return CLC_OK;
 }
@@ -445,9 +488,9 @@ int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
   auto body = [&]() -> int {
     int rc2 = alloc_points(p);
     if (rc2 != CLC_OK) return rc2;
-    CLC_CUDA(cudaMalloc(&p->frame_pose, sizeof(double) * 7 * std::max<int64_t>(N, 1)));
-    CLC_CUDA(cudaMalloc(&p->plane, sizeof(double) * 4 * std::max<int64_t>(N, 1)));
-    CLC_CUDA(cudaMalloc(&p->offsets, sizeof(int64_t) * (N + 1)));
+    CLC_CUDA(cudaMallocAsync(&p->frame_pose, sizeof(double) * 7 * std::max<int64_t>(N, 1), p->stream));
+    CLC_CUDA(cudaMallocAsync(&p->plane, sizeof(double) * 4 * std::max<int64_t>(N, 1), p->stream));
+    CLC_CUDA(cudaMallocAsync(&p->offsets, sizeof(int64_t) * (N + 1), p->stream));
     if (N > 0) {
       CLC_CUDA(cudaMemcpyAsync(p->frame_pose, d->frame_pose, sizeof(double) * 7 * N, cudaMemcpyHostToDevice, p->stream));
       CLC_CUDA(cudaMemcpyAsync(p->offsets, d->offsets, sizeof(int64_t) * (N + 1), cudaMemcpyHostToDevice, p->stream));
@@ -455,8 +498,8 @@ int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
       CLC_CUDA(cudaMemsetAsync(p->offsets, 0, sizeof(int64_t), p->stream));
     }
     if (p->n_edges > 0) {
-      CLC_CUDA(cudaMalloc(&p->edge_plane, sizeof(double) * 4 * p->n_edges));
-      CLC_CUDA(cudaMalloc(&p->edge_pt, sizeof(double) * 3 * p->n_edges));
+      CLC_CUDA(cudaMallocAsync(&p->edge_plane, sizeof(double) * 4 * p->n_edges, p->stream));
+      CLC_CUDA(cudaMallocAsync(&p->edge_pt, sizeof(double) * 3 * p->n_edges, p->stream));
       // [n_frames*6] front,back == [n_edges*3]
       CLC_CUDA(cudaMemcpyAsync(p->edge_pt, d->edge_points, sizeof(double) * 3 * p->n_edges, cudaMemcpyHostToDevice, p->stream));
     }
@@ -464,7 +507,7 @@ int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
     if (P > 0) {
       const int64_t chunk = std::min<int64_t>(P, (int64_t)8 << 20);  // 8 Mi points = 192 MiB of AoS per stage
       double* stage = nullptr;
-      CLC_CUDA(cudaMalloc(&stage, sizeof(double) * 3 * chunk));
+      CLC_CUDA(cudaMallocAsync(&stage, sizeof(double) * 3 * chunk, p->stream));
       int status = CLC_OK;
       for (int64_t b = 0; b < P && status == CLC_OK; b += chunk) {
         const int64_t n = std::min(chunk, P - b);
@@ -476,7 +519,7 @@ int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
         if (e != cudaSuccess) status = fail(CLC_ERR_CUDA, cudaGetErrorString(e));
       }
       cudaStreamSynchronize(p->stream);
-      cudaFree(stage);
+      cudaFreeAsync(stage, p->stream);
       if (status != CLC_OK) return status;
     }
     return finish_create(p);
@@ -506,12 +549,12 @@ int clc_problem_create_synthetic(clc_problem** out, const clc_synthetic_desc* d)
   auto body = [&]() -> int {
     int rc2 = alloc_points(p);
     if (rc2 != CLC_OK) return rc2;
-    CLC_CUDA(cudaMalloc(&p->frame_pose, sizeof(double) * 7 * std::max<int64_t>(N, 1)));
-    CLC_CUDA(cudaMalloc(&p->plane, sizeof(double) * 4 * std::max<int64_t>(N, 1)));
-    CLC_CUDA(cudaMalloc(&p->offsets, sizeof(int64_t) * (N + 1)));
+    CLC_CUDA(cudaMallocAsync(&p->frame_pose, sizeof(double) * 7 * std::max<int64_t>(N, 1), p->stream));
+    CLC_CUDA(cudaMallocAsync(&p->plane, sizeof(double) * 4 * std::max<int64_t>(N, 1), p->stream));
+    CLC_CUDA(cudaMallocAsync(&p->offsets, sizeof(int64_t) * (N + 1), p->stream));
     if (p->n_edges > 0) {
-      CLC_CUDA(cudaMalloc(&p->edge_plane, sizeof(double) * 4 * p->n_edges));
-      CLC_CUDA(cudaMalloc(&p->edge_pt, sizeof(double) * 3 * p->n_edges));
+      CLC_CUDA(cudaMallocAsync(&p->edge_plane, sizeof(double) * 4 * p->n_edges, p->stream));
+      CLC_CUDA(cudaMallocAsync(&p->edge_pt, sizeof(double) * 3 * p->n_edges, p->stream));
     }
     if (N > 0) {
       clc::clc_gen_frames_kernel<<<(unsigned)((N + 127) / 128), 128, 0, p->stream>>>(
@@ -560,14 +603,14 @@ int clc_problem_download(const clc_problem* p, double* frame_pose, int64_t* offs
     CLC_CUDA(cudaMemcpy(edge_points, p->edge_pt, sizeof(double) * 3 * p->n_edges, cudaMemcpyDeviceToHost));
   if (points && p->n_points > 0) {
     double* aos = nullptr;
-    CLC_CUDA(cudaMalloc(&aos, sizeof(double) * 3 * p->n_points));
+    CLC_CUDA(cudaMallocAsync(&aos, sizeof(double) * 3 * p->n_points, p->stream));
     clc::clc_soa_to_aos_kernel<<<(unsigned)((p->n_points + 255) / 256), 256, 0, p->stream>>>(p->x, p->y, p->z, 0,
                                                                                           p->n_points, aos);
     g_launches.fetch_add(1);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(points, aos, sizeof(double) * 3 * p->n_points, cudaMemcpyDeviceToHost, p->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
-    cudaFree(aos);
+    cudaFreeAsync(aos, p->stream);
     if (e != cudaSuccess) return fail(CLC_ERR_CUDA, cudaGetErrorString(e));
   }
   return CLC_OK;
@@ -848,7 +891,7 @@ int clc_bench_eval(clc_problem* p, const double pose7[7], int n, int flush_l2, f
   if (rc != CLC_OK) return rc;
   if (flush_l2 && !p->flush_buf) {
     p->flush_n = ((int64_t)256 << 20) / sizeof(double);  // 256 MiB > 126 MB of L2
-    CLC_CUDA(cudaMalloc(&p->flush_buf, sizeof(double) * p->flush_n));
+    CLC_CUDA(cudaMallocAsync(&p->flush_buf, sizeof(double) * p->flush_n, p->stream));
   }
   CLC_CUDA(cudaMemcpyAsync(p->pose, pose7, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
   std::vector<cudaEvent_t> ev(2 * (size_t)n);
@@ -882,12 +925,12 @@ int clc_debug_sweep_timing(clc_problem* p, const double pose7[7], int with_lm, i
   if (rc != CLC_OK) return rc;
   if (grid_out) *grid_out = p->grid;
   const size_t bytes = sizeof(unsigned long long) * 8 * (size_t)p->grid;
-  CLC_CUDA(cudaMalloc(&p->timing, bytes));
+  CLC_CUDA(cudaMallocAsync(&p->timing, bytes, p->stream));
   CLC_CUDA(cudaMemsetAsync(p->timing, 0, bytes, p->stream));
   if (flush_l2) {
     if (!p->flush_buf) {
       p->flush_n = ((int64_t)256 << 20) / sizeof(double);
-      CLC_CUDA(cudaMalloc(&p->flush_buf, sizeof(double) * p->flush_n));
+      CLC_CUDA(cudaMallocAsync(&p->flush_buf, sizeof(double) * p->flush_n, p->stream));
     }
     clc::clc_flush_kernel<<<p->num_sms * 4, 256, 0, p->stream>>>(p->flush_buf, p->flush_n, 1.0);
     CLC_LAUNCH_CHECK();
@@ -902,7 +945,7 @@ int clc_debug_sweep_timing(clc_problem* p, const double pose7[7], int with_lm, i
   rc = launch_sweep(p, clc::kModeLM, p->use_loss != 0, p->n_edges > 0, p->pose, nullptr, with_lm ? p->lm : nullptr);
   cudaError_t e = cudaMemcpyAsync(stamps, p->timing, bytes, cudaMemcpyDeviceToHost, p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
-  cudaFree(p->timing);
+  cudaFreeAsync(p->timing, p->stream);
   p->timing = nullptr;
   if (rc != CLC_OK) return rc;
   if (e != cudaSuccess) return fail(CLC_ERR_CUDA, cudaGetErrorString(e));
