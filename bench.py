@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--beams", type=int, default=BEAMS)
     ap.add_argument("--kernel-launches", type=int, default=100, help="timed launches of the sweep kernel for the roofline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: ncclAllReduce between kernels instead of the fused peer exchange")
     ap.add_argument("--no-config3", action="store_true", help="skip the supplementary 4.8 GB (configs[2]) measurement")
     return ap.parse_args()
 
@@ -259,6 +260,14 @@ def run_ours(args):
         uid = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         comm = Comm(uid[0], world, rank, device=local_rank)
+
+        def all_gather(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return out
+
+        if not args.nccl_allreduce:
+            comm.enable_p2p(all_gather)  # fused in-kernel all-reduce over NVLink peer memory
         prob.attach_comm(comm)
     opt = default_options()
 
@@ -389,7 +398,9 @@ def run_ours(args):
             "config": {"workload": f"BASELINE configs[1]: {args.frames} frames x {args.beams} points per GPU "
                                    f"({frames_total} frames total), calibr_simulation generator (exact-M), sigma={SIGMA} m, "
                                    f"identity start, full LM solve to Ceres convergence",
-                       "sharding": f"frames by rank, {world} rank(s), 28-double NCCL all-reduce per sweep" if world > 1 else "single GPU",
+                       "sharding": (f"frames by rank, {world} rank(s), 28-double all-reduce per sweep: " +
+                                    ("ncclAllReduce between kernels" if args.nccl_allreduce else
+                                     "fused into the sweep kernel (NVLink peer stores + flags, rank-order sum)")) if world > 1 else "single GPU",
                        "l2": f"inputs ({alg_bytes / 1e6:.0f} MB per GPU) larger than the 126 MB L2; roofline leg flushes L2 between launches",
                        "lm": "one fused residual+Jacobian+reduce sweep per LM iteration (speculative Jacobian at the candidate)"},
             "lm_iters_per_s": lm_iters_per_s, "sweeps_per_solve": sweeps / args.steps, "lm_iterations_per_solve": iters / args.steps,

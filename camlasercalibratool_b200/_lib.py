@@ -124,6 +124,8 @@ SIGNATURES = {
     "clc_comm_unique_id": (C.c_int, [_P]),
     "clc_comm_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, C.c_int]),
     "clc_comm_destroy": (C.c_int, [_P]),
+    "clc_comm_p2p_export": (C.c_int, [_P, _P]),
+    "clc_comm_p2p_import": (C.c_int, [_P, _P]),
     "clc_problem_attach_comm": (C.c_int, [_P, _P]),
     "clc_problem_set_allreduce_mode": (C.c_int, [_P, C.c_int]),
     "clc_bench_eval": (C.c_int, [_P, c_double_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),

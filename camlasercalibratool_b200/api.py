@@ -183,6 +183,10 @@ class Problem:
         return T.reshape(4, 4), bool(un.value), AtA, Atb
 
     # ---- multi-GPU ----
+    def set_allreduce_mode(self, mode: int):
+        """0 = NCCL all-reduce between kernels, 1 = fused in-kernel peer exchange (default once p2p is enabled)."""
+        _lib.check(self._L.clc_problem_set_allreduce_mode(self._h, int(mode)), "clc_problem_set_allreduce_mode")
+
     def attach_comm(self, comm: "Comm | None"):
         """Borrow a communicator: every sweep's 28 sums are then all-reduced over its ranks."""
         self._comm = comm  # keep it alive
@@ -205,6 +209,23 @@ class Comm:
         buf = C.create_string_buffer(unique_id, 128)
         _lib.check(self._L.clc_comm_create(C.byref(self._h), buf, int(nranks), int(rank), int(device)), "clc_comm_create")
         self.nranks, self.rank = int(nranks), int(rank)
+
+    def p2p_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this rank's mailbox (for the fused in-kernel all-reduce over NVLink)."""
+        buf = C.create_string_buffer(64)
+        _lib.check(self._L.clc_comm_p2p_export(self._h, buf), "clc_comm_p2p_export")
+        return buf.raw
+
+    def p2p_import(self, handles):
+        """handles: the exported handles of all ranks, in rank order."""
+        blob = b"".join(handles)
+        if len(blob) != 64 * self.nranks:
+            raise ValueError("need one 64-byte handle per rank")
+        _lib.check(self._L.clc_comm_p2p_import(self._h, C.create_string_buffer(blob, len(blob))), "clc_comm_p2p_import")
+
+    def enable_p2p(self, all_gather):
+        """all_gather(bytes) -> list[bytes] over the ranks (e.g. torch.distributed.all_gather_object)."""
+        self.p2p_import(all_gather(self.p2p_export()))
 
     def close(self):
         if self._h is not None:

@@ -216,6 +216,13 @@ void pinned_release(PinnedBlock* b) {
 struct clc_comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0, device = 0;
+  // fused peer exchange: one cudaMalloc block per rank = mailbox [2][nranks][kMailboxSlot] doubles, then flags [2][nranks]
+  void* p2p_block = nullptr;
+  void* peer_block[clc::kMaxRanks] = {};
+  bool p2p_ready = false;
+  size_t mailbox_bytes() const { return sizeof(double) * 2 * (size_t)nranks * clc::kMailboxSlot; }
+  size_t flags_bytes() const { return sizeof(unsigned long long) * 2 * (size_t)nranks; }
+  size_t block_bytes() const { return mailbox_bytes() + flags_bytes() + sizeof(unsigned long long); }  // + exchange counter
 };
 
 struct clc_problem {
@@ -248,8 +255,10 @@ struct clc_problem {
   int* h_done = nullptr;
   clc::LmState* h_lm = nullptr;
   // communicator (borrowed)
+  clc_comm* comm_obj = nullptr;
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  int* p2p_error = nullptr;
   int allreduce_mode = 0;
   int64_t per_warp = 0;
 };
@@ -279,8 +288,9 @@ int set_device(const clc_problem* p) {
 }
 
 // one K1 launch on the problem's stream
+// collective: the sums of this launch are to be all-reduced (in-kernel when the peer path is active)
 int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* d_pose, const int* d_done,
-                 clc::LmState* d_lm) {
+                 clc::LmState* d_lm, bool collective = true) {
   clc::SweepArgs a;
   a.pose7 = d_pose;
   a.done = d_done;
@@ -291,6 +301,20 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
   a.use_loss = loss ? 1 : 0;
   a.use_edges = edges ? 1 : 0;
   a.timing = p->timing;
+  a.nranks = 1;
+  a.rank = 0;
+  a.seq_counter = nullptr;
+  a.error = p->p2p_error;
+  if (p->nranks > 1 && p->allreduce_mode == 1 && collective) {
+    clc_comm* c = p->comm_obj;
+    a.nranks = c->nranks;
+    a.rank = c->rank;
+    a.seq_counter = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->p2p_block) + c->mailbox_bytes() + c->flags_bytes());
+    for (int r = 0; r < c->nranks; ++r) {
+      a.peer_mailbox[r] = static_cast<double*>(c->peer_block[r]);
+      a.peer_flags[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->peer_block[r]) + c->mailbox_bytes());
+    }
+  }
   const clc::ProblemView v = make_view(p);
   if (mode == clc::kModeClosedForm) {
     clc::clc_sweep_kernel<false, clc::kModeClosedForm><<<p->grid, clc::kThreads, clc::kDynSmemBytes, p->stream>>>(v, a);
@@ -304,8 +328,18 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
 }
 
 int allreduce_sums(clc_problem* p, int count) {
-  if (p->nranks <= 1) return CLC_OK;
+  if (p->nranks <= 1 || p->allreduce_mode == 1) return CLC_OK;  // single rank, or already reduced inside the kernel
   CLC_NCCL(nccl_api()->AllReduce(p->sums, p->sums, (size_t)count, ncclDouble, ncclSum, p->comm, p->stream));
+  return CLC_OK;
+}
+
+// a peer that never answered the in-kernel exchange (5 s time-out) is an error, not a hang
+int check_p2p_error(clc_problem* p) {
+  if (p->nranks <= 1 || p->allreduce_mode != 1) return CLC_OK;
+  int err = 0;
+  CLC_CUDA(cudaMemcpyAsync(&err, p->p2p_error, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  if (err) return fail(CLC_ERR_NCCL, "peer exchange timed out: a rank did not reach the collective");
   return CLC_OK;
 }
 
@@ -348,6 +382,8 @@ int finish_create(clc_problem* p) {
   CLC_CUDA(cudaMallocAsync(&p->pose, sizeof(double) * 8, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->ticket, sizeof(unsigned int), p->stream));
   CLC_CUDA(cudaMallocAsync(&p->lm, sizeof(clc::LmState), p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->p2p_error, sizeof(int), p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->p2p_error, 0, sizeof(int), p->stream));
   CLC_CUDA(cudaMemsetAsync(p->ticket, 0, sizeof(unsigned int), p->stream));
   CLC_CUDA(cudaMemsetAsync(p->sums, 0, sizeof(double) * clc::kMaxOut, p->stream));
   p->pinned = pinned_acquire();
@@ -452,7 +488,7 @@ int clc_problem_destroy(clc_problem* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->stream) {
     void* bufs[] = {p->x, p->y, p->z, p->frame_pose, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
-                    p->partials, p->sums, p->pose, p->ticket, p->lm, p->flush_buf};
+                    p->partials, p->sums, p->pose, p->ticket, p->lm, p->flush_buf, p->p2p_error};
     for (void* b : bufs)
       if (b) cudaFreeAsync(b, p->stream);  // back to the device's memory pool: re-creating a problem is cheap
     cudaStreamSynchronize(p->stream);
@@ -634,7 +670,7 @@ static int eval_common(clc_problem* p, const double pose7[7], bool loss, bool ed
   if (rc != CLC_OK) return rc;
   CLC_CUDA(cudaMemcpyAsync(p->h_sums, p->sums, sizeof(double) * count, cudaMemcpyDeviceToHost, p->stream));
   CLC_CUDA(cudaStreamSynchronize(p->stream));
-  return CLC_OK;
+  return check_p2p_error(p);
 }
 
 static void unpack_H(const double* sums, double* H36) {
@@ -743,7 +779,7 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
   CLC_CUDA(cudaEventCreate(&ev1));
   CLC_CUDA(cudaMemcpyAsync(p->lm, p->h_lm, sizeof(clc::LmState), cudaMemcpyHostToDevice, p->stream));
   CLC_CUDA(cudaEventRecord(ev0, p->stream));
-  const bool fused_update = (p->nranks <= 1);
+  const bool fused_update = (p->nranks <= 1) || p->allreduce_mode == 1;
   const bool loss = p->use_loss != 0, edges = p->n_edges > 0;
   // every LM iteration needs exactly one sweep; invalid steps need none -> at most max_iterations + 1 sweeps
   const int max_sweeps = opt.max_num_iterations + 2;
@@ -773,6 +809,8 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
   CLC_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
+  rc = check_p2p_error(p);
+  if (rc != CLC_OK) return rc;
 
   const clc::LmState& s = *p->h_lm;
   for (int i = 0; i < 7; ++i) pose7[i] = s.x[i];  // the last accepted point (a terminating candidate is not applied)
@@ -851,8 +889,44 @@ int clc_comm_create(clc_comm** out, const void* id128, int nranks, int rank, int
   return CLC_OK;
 }
 
+int clc_comm_p2p_export(clc_comm* c, void* handle64) {
+  if (!c || !handle64) return fail(CLC_ERR_INVALID, "NULL argument");
+  if (c->nranks > clc::kMaxRanks) return fail(CLC_ERR_INVALID, "too many ranks for the peer path");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CLC_CUDA(cudaSetDevice(c->device));
+  if (!c->p2p_block) {
+    CLC_CUDA(cudaMalloc(&c->p2p_block, c->block_bytes()));  // cudaMalloc (not the pool): IPC needs a real allocation
+    CLC_CUDA(cudaMemset(c->p2p_block, 0, c->block_bytes()));
+  }
+  cudaIpcMemHandle_t h;
+  CLC_CUDA(cudaIpcGetMemHandle(&h, c->p2p_block));
+  std::memcpy(handle64, &h, sizeof(h));
+  return CLC_OK;
+}
+
+int clc_comm_p2p_import(clc_comm* c, const void* handles) {
+  if (!c || !handles) return fail(CLC_ERR_INVALID, "NULL argument");
+  if (!c->p2p_block) return fail(CLC_ERR_STATE, "clc_comm_p2p_export must be called first");
+  CLC_CUDA(cudaSetDevice(c->device));
+  for (int r = 0; r < c->nranks; ++r) {
+    if (r == c->rank) {
+      c->peer_block[r] = c->p2p_block;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(handles) + 64 * (size_t)r, sizeof(h));
+    CLC_CUDA(cudaIpcOpenMemHandle(&c->peer_block[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  c->p2p_ready = true;
+  return CLC_OK;
+}
+
 int clc_comm_destroy(clc_comm* c) {
   if (!c) return CLC_OK;
+  cudaSetDevice(c->device);
+  for (int r = 0; r < c->nranks; ++r)
+    if (r != c->rank && c->peer_block[r]) cudaIpcCloseMemHandle(c->peer_block[r]);
+  if (c->p2p_block) cudaFree(c->p2p_block);
   if (c->comm && nccl_api()->handle) {
     cudaSetDevice(c->device);
     nccl_api()->CommDestroy(c->comm);
@@ -864,21 +938,27 @@ int clc_comm_destroy(clc_comm* c) {
 int clc_problem_attach_comm(clc_problem* p, clc_comm* c) {
   if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
   if (!c) {
+    p->comm_obj = nullptr;
     p->comm = nullptr;
     p->nranks = 1;
     p->rank = 0;
+    p->allreduce_mode = 0;
     return CLC_OK;
   }
   if (c->device != p->device) return fail(CLC_ERR_INVALID, "communicator and problem live on different devices");
+  p->comm_obj = c;
   p->comm = c->comm;
   p->nranks = c->nranks;
   p->rank = c->rank;
+  p->allreduce_mode = c->p2p_ready ? 1 : 0;
   return CLC_OK;
 }
 
 int clc_problem_set_allreduce_mode(clc_problem* p, int mode) {
   if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
-  if (mode != 0) return fail(CLC_ERR_INVALID, "unknown all-reduce mode");
+  if (mode != 0 && mode != 1) return fail(CLC_ERR_INVALID, "unknown all-reduce mode");
+  if (mode == 1 && !(p->comm_obj && p->comm_obj->p2p_ready))
+    return fail(CLC_ERR_STATE, "peer exchange not initialised (clc_comm_p2p_export / clc_comm_p2p_import)");
   p->allreduce_mode = mode;
   return CLC_OK;
 }
@@ -905,7 +985,7 @@ int clc_bench_eval(clc_problem* p, const double pose7[7], int n, int flush_l2, f
       CLC_LAUNCH_CHECK();
     }
     CLC_CUDA(cudaEventRecord(ev[2 * i], p->stream));
-    rc = launch_sweep(p, clc::kModeLM, loss, edges, p->pose, nullptr, nullptr);
+    rc = launch_sweep(p, clc::kModeLM, loss, edges, p->pose, nullptr, nullptr, /*collective=*/false);
     if (rc != CLC_OK) return rc;
     CLC_CUDA(cudaEventRecord(ev[2 * i + 1], p->stream));
   }
@@ -942,7 +1022,7 @@ int clc_debug_sweep_timing(clc_problem* p, const double pose7[7], int with_lm, i
   clc::lm_init(p->h_lm, pose7, opt);
   CLC_CUDA(cudaMemcpyAsync(p->lm, p->h_lm, sizeof(clc::LmState), cudaMemcpyHostToDevice, p->stream));
   CLC_CUDA(cudaMemcpyAsync(p->pose, pose7, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
-  rc = launch_sweep(p, clc::kModeLM, p->use_loss != 0, p->n_edges > 0, p->pose, nullptr, with_lm ? p->lm : nullptr);
+  rc = launch_sweep(p, clc::kModeLM, p->use_loss != 0, p->n_edges > 0, p->pose, nullptr, with_lm ? p->lm : nullptr, /*collective=*/false);
   cudaError_t e = cudaMemcpyAsync(stamps, p->timing, bytes, cudaMemcpyDeviceToHost, p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
   cudaFreeAsync(p->timing, p->stream);

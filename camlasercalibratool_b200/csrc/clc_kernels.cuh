@@ -37,6 +37,8 @@ constexpr int kChunk = CLC_CHUNK;     // points per pipeline stage and coordinat
 constexpr int kGroups = kChunk / 64;  // 64-point groups per stage: every lane takes 2 adjacent points of each group
 constexpr int kStages = CLC_STAGES;   // bulk-copy stages in flight per warp (x 3 KiB)
 constexpr int kMaxOut = 54;           // closed-form mode: 45 + 9
+constexpr int kMaxRanks = 16;
+constexpr int kMailboxSlot = 64;      // doubles per (parity, source rank) mailbox slot (>= kMaxOut)
 constexpr int kRingDoublesPerWarp = kStages * 3 * kChunk;
 constexpr int kTileDoublesPerWarp = 32 * kTileStride;
 constexpr int kDynSmemBytes = kWarps * kRingDoublesPerWarp * 8 + kWarps * kTileDoublesPerWarp * 8 + kWarps * kStages * 8;
@@ -71,6 +73,14 @@ struct SweepArgs {
   int use_loss;
   int use_edges;
   unsigned long long* timing;  // optional [gridDim.x * 8] globaltimer stamps (profiling hook), nullptr normally
+  // fused all-reduce over NVLink peer memory (nranks > 1): every rank's last block stores its sums into every rank's
+  // mailbox, raises a flag there, waits for all flags in its own mailbox and adds the contributions in rank order
+  int nranks;
+  int rank;
+  unsigned long long* seq_counter;        // device counter of completed exchanges (local to the rank; all ranks agree)
+  double* peer_mailbox[kMaxRanks];        // peer_mailbox[r]: rank r's mailbox [2][nranks][kMailboxSlot] (IPC-mapped)
+  unsigned long long* peer_flags[kMaxRanks];  // peer_flags[r]: rank r's flags [2][nranks]
+  int* error;                             // set to 1 on a peer time-out
 };
 
 // ---- small device helpers ---------------------------------------------------------------------------------
@@ -111,6 +121,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // gpu-scope acq_rel fetch-add: releases this block's partial sums (ordered before it by the preceding block barrier)
@@ -532,13 +556,47 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
       if (k < 32) s_red[warp][k] = v; else s_acc[warp][k] = v;
     }
     __syncthreads();
+    double total = 0.0;
     if (threadIdx.x < NOUT) {
-      double v = 0.0;
       const int k = threadIdx.x;
 #pragma unroll
-      for (int wv = 0; wv < kWarps; ++wv) v += (k < 32) ? s_red[wv][k] : s_acc[wv][k];
-      args.sums[k] = v;
-      if (k < 32) s_red[0][k] = v;
+      for (int wv = 0; wv < kWarps; ++wv) total += (k < 32) ? s_red[wv][k] : s_acc[wv][k];
+    }
+    if (args.nranks > 1) {
+      // ---- fused all-reduce: NVLink stores into every rank's mailbox, flags, deterministic rank-order sum ----
+      // the sequence number lives on the device: sweeps that no-op (LM already finished) must not consume one, or two
+      // consecutive real exchanges could land in the same parity slot while a slow peer is still reading it
+      const unsigned long long seq = *args.seq_counter + 1ull;
+      const int par = (int)(seq & 1ull);
+      const int slot = par * args.nranks + args.rank;
+      if (threadIdx.x < NOUT)
+        for (int r = 0; r < args.nranks; ++r) args.peer_mailbox[r][(int64_t)slot * kMailboxSlot + threadIdx.x] = total;
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x < args.nranks) {
+        st_release_sys(args.peer_flags[threadIdx.x] + slot, seq);
+        // wait for rank threadIdx.x's contribution to arrive in my mailbox
+        const unsigned long long* my_flag = args.peer_flags[args.rank] + par * args.nranks + threadIdx.x;
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(my_flag) != seq) {
+          if (globaltimer_ns() - t0 > 5000000000ull) {  // 5 s: a peer died -- fail loudly instead of hanging
+            if (args.error != nullptr) *args.error = 1;
+            break;
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < NOUT) {
+        const double* mine = args.peer_mailbox[args.rank] + (int64_t)par * args.nranks * kMailboxSlot + threadIdx.x;
+        total = 0.0;
+        for (int r = 0; r < args.nranks; ++r) total += ld_relaxed_sys(mine + (int64_t)r * kMailboxSlot);
+      }
+      if (threadIdx.x == 0) *args.seq_counter = seq;
+    }
+    __syncthreads();
+    if (threadIdx.x < NOUT) {
+      args.sums[threadIdx.x] = total;
+      if (threadIdx.x < 32) s_red[0][threadIdx.x] = total;
     }
     __syncthreads();
     CLC_STAMP(4);

@@ -172,7 +172,14 @@ int clc_comm_unique_id(void* id128);
 int clc_comm_create(clc_comm** out, const void* id128, int nranks, int rank, int device);
 int clc_comm_destroy(clc_comm* comm);
 int clc_problem_attach_comm(clc_problem* p, clc_comm* comm);
-/* all-reduce mode: 0 = ncclAllReduce on the solve stream between the kernels (default) */
+/* Fused all-reduce over NVLink peer memory: every rank exports a 64-byte IPC handle of its mailbox, the handles of
+ * all ranks (rank order, nranks*64 bytes) are shipped to every rank by any means, and every rank imports them.  From
+ * then on the last block of every sweep kernel exchanges the 28 sums with direct peer stores and runs the LM update in
+ * the same launch (no NCCL call, no extra kernel).  Requires one process per GPU on one NVLink/NVSwitch node. */
+int clc_comm_p2p_export(clc_comm* comm, void* handle64);
+int clc_comm_p2p_import(clc_comm* comm, const void* handles /* [nranks*64] */);
+/* all-reduce mode of a problem: 0 = ncclAllReduce on the solve stream between the kernels,
+ * 1 = fused in-kernel peer exchange (needs clc_comm_p2p_import; the default once it has been called) */
 int clc_problem_set_allreduce_mode(clc_problem* p, int mode);
 
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------------- */
