@@ -216,13 +216,12 @@ void pinned_release(PinnedBlock* b) {
 struct clc_comm {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0, device = 0;
-  // fused peer exchange: one cudaMalloc block per rank = mailbox [2][nranks][kMailboxSlot] doubles, then flags [2][nranks]
+  // fused peer exchange: one cudaMalloc block per rank = mailbox [2][nranks][kMailboxSlot][2] words, then the counter
   void* p2p_block = nullptr;
   void* peer_block[clc::kMaxRanks] = {};
   bool p2p_ready = false;
-  size_t mailbox_bytes() const { return sizeof(double) * 2 * (size_t)nranks * clc::kMailboxSlot; }
-  size_t flags_bytes() const { return sizeof(unsigned long long) * 2 * (size_t)nranks; }
-  size_t block_bytes() const { return mailbox_bytes() + flags_bytes() + sizeof(unsigned long long); }  // + exchange counter
+  size_t mailbox_bytes() const { return sizeof(unsigned long long) * 2 * 2 * (size_t)nranks * clc::kMailboxSlot; }
+  size_t block_bytes() const { return mailbox_bytes() + sizeof(unsigned long long); }  // + exchange counter
 };
 
 struct clc_problem {
@@ -309,11 +308,8 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
     clc_comm* c = p->comm_obj;
     a.nranks = c->nranks;
     a.rank = c->rank;
-    a.seq_counter = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->p2p_block) + c->mailbox_bytes() + c->flags_bytes());
-    for (int r = 0; r < c->nranks; ++r) {
-      a.peer_mailbox[r] = static_cast<double*>(c->peer_block[r]);
-      a.peer_flags[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->peer_block[r]) + c->mailbox_bytes());
-    }
+    a.seq_counter = reinterpret_cast<unsigned long long*>(static_cast<char*>(c->p2p_block) + c->mailbox_bytes());
+    for (int r = 0; r < c->nranks; ++r) a.peer_mailbox[r] = static_cast<unsigned long long*>(c->peer_block[r]);
   }
   const clc::ProblemView v = make_view(p);
   if (mode == clc::kModeClosedForm) {

@@ -74,12 +74,14 @@ struct SweepArgs {
   int use_edges;
   unsigned long long* timing;  // optional [gridDim.x * 8] globaltimer stamps (profiling hook), nullptr normally
   // fused all-reduce over NVLink peer memory (nranks > 1): every rank's last block stores its sums into every rank's
-  // mailbox, raises a flag there, waits for all flags in its own mailbox and adds the contributions in rank order
+  // mailbox with a low-latency protocol -- every 8-byte word carries 32 bits of payload and the 32-bit sequence number,
+  // 8-byte stores are atomic, so no fence and no separate flag are needed -- then polls its own mailbox and adds the
+  // contributions in rank order (identical bits on every rank)
   int nranks;
   int rank;
   unsigned long long* seq_counter;        // device counter of completed exchanges (local to the rank; all ranks agree)
-  double* peer_mailbox[kMaxRanks];        // peer_mailbox[r]: rank r's mailbox [2][nranks][kMailboxSlot] (IPC-mapped)
-  unsigned long long* peer_flags[kMaxRanks];  // peer_flags[r]: rank r's flags [2][nranks]
+  unsigned long long* peer_mailbox[kMaxRanks];  // peer_mailbox[r]: rank r's mailbox (IPC-mapped),
+                                                // [2 parity][nranks source][kMailboxSlot values][2 words]
   int* error;                             // set to 1 on a peer time-out
 };
 
@@ -123,17 +125,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -567,30 +564,38 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
       // the sequence number lives on the device: sweeps that no-op (LM already finished) must not consume one, or two
       // consecutive real exchanges could land in the same parity slot while a slow peer is still reading it
       const unsigned long long seq = *args.seq_counter + 1ull;
+      const unsigned long long tag = (seq & 0xffffffffull) << 32;  // never matches the zero-initialised mailbox for seq >= 1
       const int par = (int)(seq & 1ull);
-      const int slot = par * args.nranks + args.rank;
-      if (threadIdx.x < NOUT)
-        for (int r = 0; r < args.nranks; ++r) args.peer_mailbox[r][(int64_t)slot * kMailboxSlot + threadIdx.x] = total;
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x < args.nranks) {
-        st_release_sys(args.peer_flags[threadIdx.x] + slot, seq);
-        // wait for rank threadIdx.x's contribution to arrive in my mailbox
-        const unsigned long long* my_flag = args.peer_flags[args.rank] + par * args.nranks + threadIdx.x;
+      if (threadIdx.x < NOUT) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
+        const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+        const int64_t slot = (((int64_t)par * args.nranks + args.rank) * kMailboxSlot + threadIdx.x) * 2;
+        for (int r = 0; r < args.nranks; ++r) {
+          st_relaxed_sys(args.peer_mailbox[r] + slot, w0);
+          st_relaxed_sys(args.peer_mailbox[r] + slot + 1, w1);
+        }
+        // poll my own mailbox: the contribution of every rank, added in rank order
         const unsigned long long t0 = globaltimer_ns();
-        while (ld_acquire_sys(my_flag) != seq) {
-          if (globaltimer_ns() - t0 > 5000000000ull) {  // 5 s: a peer died -- fail loudly instead of hanging
-            if (args.error != nullptr) *args.error = 1;
-            break;
+        total = 0.0;
+        bool timed_out = false;
+        for (int r = 0; r < args.nranks && !timed_out; ++r) {
+          const unsigned long long* src =
+              args.peer_mailbox[args.rank] + (((int64_t)par * args.nranks + r) * kMailboxSlot + threadIdx.x) * 2;
+          unsigned long long a0, a1;
+          for (;;) {
+            a0 = ld_relaxed_sys(src);
+            a1 = ld_relaxed_sys(src + 1);
+            if ((a0 & 0xffffffff00000000ull) == tag && (a1 & 0xffffffff00000000ull) == tag) break;
+            if (globaltimer_ns() - t0 > 5000000000ull) {  // 5 s: a peer died -- fail loudly instead of hanging
+              if (args.error != nullptr) *args.error = 1;
+              timed_out = true;
+              break;
+            }
           }
+          total += __longlong_as_double((long long)((a1 << 32) | (a0 & 0xffffffffull)));
         }
       }
       __syncthreads();
-      if (threadIdx.x < NOUT) {
-        const double* mine = args.peer_mailbox[args.rank] + (int64_t)par * args.nranks * kMailboxSlot + threadIdx.x;
-        total = 0.0;
-        for (int r = 0; r < args.nranks; ++r) total += ld_relaxed_sys(mine + (int64_t)r * kMailboxSlot);
-      }
       if (threadIdx.x == 0) *args.seq_counter = seq;
     }
     __syncthreads();
