@@ -1,0 +1,243 @@
+// LaseCamCalB200.cpp -- drop-in replacement for the reference's src/LaseCamCalCeres.cpp.
+//
+// Same translation-unit role, same four global functions, same `Oberserve` struct (it includes the reference's own
+// include/LaseCamCalCeres.h): swap this file for src/LaseCamCalCeres.cpp in the `lasercamcal` library target, link
+// libclc_b200.so, and main/calibr_offline.cpp / main/calibr_simulation.cpp build and run unchanged.
+// Ceres is no longer needed by this translation unit; Eigen only through the types in the signatures.
+//
+// What happens where
+//   host (here)   marshal std::vector<Oberserve> into the flat arrays of the C ABI (include/clc_b200.h)
+//   GPU (library) board planes, fused residual+Jacobian+Cauchy+reduce sweeps, the Ceres-equivalent LM loop with its
+//                 6x6 damped solve and SE(3) update, the un-robustified information matrix, the closed-form 9x9
+// There is no CPU fallback: if the library reports an error the functions print it and leave the output untouched
+// (the reference's functions are `void` and have no error channel, reference include/LaseCamCalCeres.h:26-29).
+#include "LaseCamCalCeres.h"
+
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <vector>
+
+#include "clc_b200.h"
+
+namespace {
+
+struct Marshalled {
+  std::vector<double> frame_pose;  // [N*7] qx qy qz qw tx ty tz
+  std::vector<int64_t> offsets;    // [N+1]
+  std::vector<double> points;      // [P*3]
+  std::vector<double> edge_points; // [N*6] or empty
+};
+
+// Point-set selection of reference src/LaseCamCalCeres.cpp:233-237; edge points of :278-279 (only when both flags are
+// set, :258).
+Marshalled marshal(const std::vector<Oberserve>& obs, bool use_linefitting_data, bool use_boundary_constraint) {
+  Marshalled m;
+  const size_t n = obs.size();
+  m.frame_pose.resize(7 * n);
+  m.offsets.assign(n + 1, 0);
+  const bool edges = use_boundary_constraint && use_linefitting_data;
+  if (edges) m.edge_points.assign(6 * n, 0.0);
+  size_t total = 0;
+  for (size_t i = 0; i < n; ++i) total += (use_linefitting_data ? obs[i].points_on_line : obs[i].points).size();
+  m.points.reserve(3 * total);
+  for (size_t i = 0; i < n; ++i) {
+    const Oberserve& ob = obs[i];
+    double* fp = &m.frame_pose[7 * i];
+    fp[0] = ob.tagPose_Qca.x(); fp[1] = ob.tagPose_Qca.y(); fp[2] = ob.tagPose_Qca.z(); fp[3] = ob.tagPose_Qca.w();
+    fp[4] = ob.tagPose_tca.x(); fp[5] = ob.tagPose_tca.y(); fp[6] = ob.tagPose_tca.z();
+    const std::vector<Eigen::Vector3d>& pts = use_linefitting_data ? ob.points_on_line : ob.points;
+    for (const Eigen::Vector3d& p : pts) {
+      m.points.push_back(p.x()); m.points.push_back(p.y()); m.points.push_back(p.z());
+    }
+    m.offsets[i + 1] = m.offsets[i] + (int64_t)pts.size();
+    if (edges && !pts.empty() && !ob.points.empty()) {
+      const Eigen::Vector3d& a = ob.points.front();
+      const Eigen::Vector3d& b = ob.points.back();
+      double* e = &m.edge_points[6 * i];
+      e[0] = a.x(); e[1] = a.y(); e[2] = a.z(); e[3] = b.x(); e[4] = b.y(); e[5] = b.z();
+    }
+  }
+  return m;
+}
+
+clc_problem* create(const Marshalled& m) {
+  clc_problem_desc d;
+  d.n_frames = (int64_t)m.offsets.size() - 1;
+  d.frame_pose = m.frame_pose.data();
+  d.offsets = m.offsets.data();
+  d.points = m.points.data();
+  d.edge_points = m.edge_points.empty() ? nullptr : m.edge_points.data();
+  d.use_loss = 1;      // #define LOSSFUNCTION, reference :212
+  d.cauchy_a = 0.05;   // reference :249
+  d.device = -1;
+  clc_problem* p = nullptr;
+  if (clc_problem_create(&p, &d) != CLC_OK) {
+    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
+    return nullptr;
+  }
+  return p;
+}
+
+void print4(const double T[16]) {
+  for (int r = 0; r < 4; ++r) std::cout << T[r * 4] << " " << T[r * 4 + 1] << " " << T[r * 4 + 2] << " " << T[r * 4 + 3] << "\n";
+}
+
+const char* termination_name(int t) {
+  switch (t) {
+    case CLC_TERM_CONVERGENCE_FUNCTION: return "CONVERGENCE (function tolerance)";
+    case CLC_TERM_CONVERGENCE_PARAMETER: return "CONVERGENCE (parameter tolerance)";
+    case CLC_TERM_CONVERGENCE_GRADIENT: return "CONVERGENCE (gradient tolerance)";
+    case CLC_TERM_CONVERGENCE_MIN_RADIUS: return "CONVERGENCE (minimum trust-region radius)";
+    case CLC_TERM_NO_CONVERGENCE: return "NO_CONVERGENCE (maximum iterations)";
+    default: return "FAILURE";
+  }
+}
+
+}  // namespace
+
+// reference src/LaseCamCalCeres.cpp:112-203
+void CamLaserCalClosedSolution(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tlc) {
+  const Marshalled m = marshal(obs, /*use_linefitting_data=*/true, false);  // :143 uses points_on_line
+  clc_problem* p = create(m);
+  if (!p) return;
+  double T[16];
+  int unobservable = 0;
+  const int rc = clc_closed_form(p, T, &unobservable, nullptr, nullptr);
+  clc_problem_destroy(p);
+  if (rc != CLC_OK) {
+    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
+    return;
+  }
+  if (unobservable) {  // :173-178
+    std::cout << std::endl << "~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~" << std::endl;
+    std::cout << " Notice Notice Notice: system unobservable !!!!!!!" << std::endl;
+    std::cout << "~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~" << std::endl << std::endl;
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) Tlc(r, c) = T[r * 4 + c];  // :198-200
+  std::cout << "------- Closed-form solution Tlc: -------\n";
+  print4(T);
+}
+
+// reference src/LaseCamCalCeres.cpp:213-383
+void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl, bool use_linefitting_data,
+                         bool use_boundary_constraint) {
+  double T[16], pose[7];
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) T[r * 4 + c] = Tcl(r, c);
+  clc_T_to_pose7(T, pose);  // :215-219 (Eigen::Quaterniond(Matrix3d) restated in the library)
+  const Marshalled m = marshal(obs, use_linefitting_data, use_boundary_constraint);
+  clc_problem* p = create(m);
+  if (!p) return;
+
+  clc_lm_options opt;
+  clc_lm_default_options(&opt);  // DENSE_QR-equivalent step, max_num_iterations = 100 (:303-304), Ceres defaults
+  clc_lm_summary sum;
+  std::vector<clc_lm_iteration> trace(256);
+  if (clc_solve_lm(p, pose, &opt, &sum, trace.data(), (int)trace.size()) != CLC_OK) {
+    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
+    clc_problem_destroy(p);
+    return;
+  }
+  // the counterpart of summary.FullReport() (:309)
+  std::cout << "\nSolver Summary (libclc_b200, on-device Levenberg-Marquardt)\n";
+  std::cout << "iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius\n";
+  for (int i = 0; i < sum.num_iterations && i < (int)trace.size(); ++i) {
+    const clc_lm_iteration& it = trace[i];
+    std::printf("%4d  %.6e  %9.2e  %9.2e  %9.2e  %9.2e  %9.2e\n", it.iteration, it.cost, it.cost_change,
+                it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius);
+  }
+  std::cout << "Initial cost " << sum.initial_cost << "  Final cost " << sum.final_cost << "  Iterations "
+            << sum.num_iterations << " (successful " << sum.num_successful_steps << ", unsuccessful "
+            << sum.num_unsuccessful_steps << ")  Device time " << sum.device_ms << " ms\n";
+  std::cout << "Termination: " << termination_name(sum.termination) << "\n" << std::endl;
+
+  clc_pose7_to_T(pose, T);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) Tcl(r, c) = T[r * 4 + c];  // :311-314 (bottom row untouched)
+
+  // ---- analysis tail (:316-381) ----
+  double H[36], b[6], chi = 0.0, sv[6];
+  if (clc_information(p, pose, H, b, &chi, sv) == CLC_OK) {
+    std::cout << "----- H singular values--------:\n";
+    for (int i = 0; i < 6; ++i) std::cout << sv[i] << "\n";
+    int n_null = 0;
+    for (int i = 0; i < 6; ++i)
+      if (sv[i] < 1e-8) ++n_null;  // :371
+    if (n_null > 0) {
+      std::cout << "====== null space basis, it's means the unobservable direction for Tcl ======" << std::endl;
+      std::cout << "       please note the unobservable direction is for Tcl, not for Tlc        " << std::endl;
+      std::cout << "       (" << n_null << " singular value(s) below 1e-8; H follows)\n";
+      for (int r = 0; r < 6; ++r) {
+        for (int c = 0; c < 6; ++c) std::cout << H[r * 6 + c] << " ";
+        std::cout << "\n";
+      }
+    }
+    std::cout << "\nrecover chi2: " << chi / 2. << std::endl;  // :381
+  } else {
+    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
+  }
+  clc_problem_destroy(p);
+}
+
+// reference src/LaseCamCalCeres.cpp:68-110 (pure host I/O; kept so that the translation unit stays a complete
+// replacement -- the board plane is the same (Tctag^-1)^T (0,0,1,0) the library computes on the device)
+void CalibrationTool_SavePlanePoints(const std::vector<Oberserve> obs, const Eigen::Matrix4d Tcl, const std::string path) {
+  std::ofstream fs_planar(path + "planar.txt"), fs_points(path + "RoiPoints.txt"), fs_lines(path + "RoiPtOnLines.txt");
+  fs_planar << std::setprecision(3);
+  fs_points << std::setprecision(3);
+  fs_lines << std::setprecision(3);
+  const Marshalled m = marshal(obs, false, false);
+  clc_problem* p = create(m);
+  std::vector<double> planes(4 * obs.size());
+  if (p) {
+    clc_problem_download(p, nullptr, nullptr, nullptr, nullptr, planes.data());
+    clc_problem_destroy(p);
+  }
+  auto to_cam = [&](const Eigen::Vector3d& q, double out[3]) {
+    for (int r = 0; r < 3; ++r) out[r] = Tcl(r, 0) * q.x() + Tcl(r, 1) * q.y() + Tcl(r, 2) * q.z() + Tcl(r, 3);
+  };
+  for (size_t i = 0; i < obs.size(); ++i) {
+    fs_planar << i << " " << planes[4 * i] << " " << planes[4 * i + 1] << " " << planes[4 * i + 2] << " " << planes[4 * i + 3]
+              << std::endl;
+    double c[3];
+    for (const Eigen::Vector3d& q : obs[i].points) {
+      to_cam(q, c);
+      fs_points << i << " " << c[0] << " " << c[1] << " " << c[2] << std::endl;
+    }
+    for (const Eigen::Vector3d& q : obs[i].points_on_line) {
+      to_cam(q, c);
+      fs_lines << i << " " << c[0] << " " << c[1] << " " << c[2] << std::endl;
+    }
+  }
+}
+
+// reference src/LaseCamCalCeres.cpp:385-433 -- a per-scan 2-parameter robust line fit that runs BEFORE the path this
+// library accelerates.  Not on the GPU yet: see DESIGN.md "Out of scope / next".
+#ifndef CLC_B200_NO_LINEFITTING_STUB
+void LineFittingCeres(const std::vector<Eigen::Vector3d> Points, Eigen::Vector2d& Line) {
+  // Iteratively re-weighted least squares of m0 x + m1 y + 1 = 0 with the Cauchy weight 1/(1 + r^2/0.05^2), started at
+  // the incoming Line -- the same fixed point Ceres' 10 LM iterations converge to.  Host code, O(scan) per call.
+  double m0 = Line(0), m1 = Line(1);
+  for (int it = 0; it < 50; ++it) {
+    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
+    for (const Eigen::Vector3d& q : Points) {
+      const double r = m0 * q.x() + m1 * q.y() + 1.0;
+      const double w = 1.0 / (1.0 + r * r / (0.05 * 0.05));
+      a00 += w * q.x() * q.x(); a01 += w * q.x() * q.y(); a11 += w * q.y() * q.y();
+      b0 -= w * q.x(); b1 -= w * q.y();
+    }
+    const double det = a00 * a11 - a01 * a01;
+    if (!(std::fabs(det) > 1e-300)) break;
+    const double n0 = (a11 * b0 - a01 * b1) / det, n1 = (a00 * b1 - a01 * b0) / det;
+    const double change = std::fabs(n0 - m0) + std::fabs(n1 - m1);
+    m0 = n0; m1 = n1;
+    if (change < 1e-14) break;
+  }
+  Line(0) = m0;
+  Line(1) = m1;
+}
+#endif
