@@ -769,11 +769,11 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
   if (opt.max_num_iterations < 0) return fail(CLC_ERR_INVALID, "max_num_iterations < 0");
   if (opt.iterations_per_sync < 1) opt.iterations_per_sync = 1;
 
-  clc::lm_init(p->h_lm, pose7, opt);
+  clc::lm_init(&p->h_lm->core, pose7, opt);
   cudaEvent_t ev0, ev1;
   CLC_CUDA(cudaEventCreate(&ev0));
   CLC_CUDA(cudaEventCreate(&ev1));
-  CLC_CUDA(cudaMemcpyAsync(p->lm, p->h_lm, sizeof(clc::LmState), cudaMemcpyHostToDevice, p->stream));
+  CLC_CUDA(cudaMemcpyAsync(&p->lm->core, &p->h_lm->core, sizeof(clc::LmCore), cudaMemcpyHostToDevice, p->stream));
   CLC_CUDA(cudaEventRecord(ev0, p->stream));
   const bool fused_update = (p->nranks <= 1) || p->allreduce_mode == 1;
   const bool loss = p->use_loss != 0, edges = p->n_edges > 0;
@@ -784,7 +784,7 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
   while (launched < max_sweeps) {
     const int batch = std::min(opt.iterations_per_sync, max_sweeps - launched);
     for (int i = 0; i < batch; ++i) {
-      rc = launch_sweep(p, clc::kModeLM, loss, edges, p->lm->cand, &p->lm->done, fused_update ? p->lm : nullptr);
+      rc = launch_sweep(p, clc::kModeLM, loss, edges, p->lm->core.cand, &p->lm->core.done, fused_update ? p->lm : nullptr);
       if (rc != CLC_OK) return rc;
       if (!fused_update) {
         rc = allreduce_sums(p, clc::kNumSums);
@@ -794,7 +794,7 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
       }
     }
     launched += batch;
-    CLC_CUDA(cudaMemcpyAsync(p->h_done, &p->lm->done, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CLC_CUDA(cudaMemcpyAsync(p->h_done, &p->lm->core.done, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CLC_CUDA(cudaStreamSynchronize(p->stream));
     if (*p->h_done != 0) break;
   }
@@ -808,7 +808,8 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
   rc = check_p2p_error(p);
   if (rc != CLC_OK) return rc;
 
-  const clc::LmState& s = *p->h_lm;
+  const clc::LmCore& s = p->h_lm->core;
+  const clc_lm_iteration* dev_trace = p->h_lm->trace;
   for (int i = 0; i < 7; ++i) pose7[i] = s.x[i];  // the last accepted point (a terminating candidate is not applied)
   if (summary) {
     summary->termination = s.done ? s.done : CLC_TERM_NO_CONVERGENCE;
@@ -823,7 +824,7 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
   }
   if (trace) {
     const int n = std::min(std::min(s.n_trace, clc::kTraceMax), trace_cap);
-    for (int i = 0; i < n; ++i) trace[i] = s.trace[i];
+    for (int i = 0; i < n; ++i) trace[i] = dev_trace[i];
   }
   return CLC_OK;
 }
@@ -1015,7 +1016,7 @@ int clc_debug_sweep_timing(clc_problem* p, const double pose7[7], int with_lm, i
   }
   clc_lm_options opt;
   clc_lm_default_options(&opt);
-  clc::lm_init(p->h_lm, pose7, opt);
+  clc::lm_init(&p->h_lm->core, pose7, opt);
   CLC_CUDA(cudaMemcpyAsync(p->lm, p->h_lm, sizeof(clc::LmState), cudaMemcpyHostToDevice, p->stream));
   CLC_CUDA(cudaMemcpyAsync(p->pose, pose7, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
   rc = launch_sweep(p, clc::kModeLM, p->use_loss != 0, p->n_edges > 0, p->pose, nullptr, with_lm ? p->lm : nullptr, /*collective=*/false);

@@ -605,13 +605,21 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     }
     __syncthreads();
     CLC_STAMP(4);
-    if (threadIdx.x == 0) {
-      *args.ticket = 0u;
-      if (MODE == kModeLM && args.lm != nullptr) {
+    if (threadIdx.x == 0) *args.ticket = 0u;
+    if (MODE == kModeLM && args.lm != nullptr) {
+      // stage the hot LM state through shared memory: one parallel round trip in, one out, instead of one per field
+      unsigned long long* s_core = reinterpret_cast<unsigned long long*>(s_dyn);  // the rings are idle by now
+      const unsigned long long* g_core = reinterpret_cast<const unsigned long long*>(&args.lm->core);
+      for (int k = threadIdx.x; k < kLmCoreWords; k += kThreads) s_core[k] = __ldcg(g_core + k);
+      __syncthreads();
+      if (threadIdx.x == 0) {
         double sums[kNumSums];
         for (int k = 0; k < kNumSums; ++k) sums[k] = s_red[0][k];
-        lm_update(args.lm, sums);
+        lm_update(reinterpret_cast<LmCore*>(s_core), args.lm->trace, sums);
       }
+      __syncthreads();
+      unsigned long long* o_core = reinterpret_cast<unsigned long long*>(&args.lm->core);
+      for (int k = threadIdx.x; k < kLmCoreWords; k += kThreads) o_core[k] = s_core[k];
     }
     CLC_STAMP(5);
   }
@@ -622,7 +630,7 @@ __global__ void clc_lm_kernel(LmState* lm, const double* sums) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double s[kNumSums];
     for (int k = 0; k < kNumSums; ++k) s[k] = sums[k];
-    lm_update(lm, s);
+    lm_update(&lm->core, lm->trace, s);
   }
 }
 

@@ -20,7 +20,9 @@ namespace clc {
 constexpr int kTraceMax = 256;
 constexpr int kNumSums = 28;  // 21 upper-tri H + 6 g + 1 cost
 
-struct LmState {
+// Hot state of the minimiser (about 600 bytes): staged through shared memory around lm_update so that the single
+// thread running it does not pay a global-memory round trip per field.
+struct LmCore {
   int done;            // CLC_TERM_*; 0 while running
   int phase;           // 0: the pending sweep evaluates the start point; 1: it evaluates a candidate
   int iteration;       // index of the last finalised iteration
@@ -39,6 +41,12 @@ struct LmState {
   double radius, decrease_factor, model_cost_change;
   double initial_cost;
   clc_lm_options opt;
+};
+static_assert(sizeof(LmCore) % 8 == 0, "LmCore is copied as 8-byte words");
+constexpr int kLmCoreWords = (int)(sizeof(LmCore) / 8);
+
+struct LmState {
+  LmCore core;
   clc_lm_iteration trace[kTraceMax];
 };
 
@@ -60,12 +68,12 @@ CLC_HD double gradient_max_norm(const double* x, const double* g) {
   return m;
 }
 
-CLC_HD void lm_record(LmState* s, const clc_lm_iteration& it) {
-  if (s->n_trace < kTraceMax) s->trace[s->n_trace] = it;
+CLC_HD void lm_record(LmCore* s, clc_lm_iteration* trace, const clc_lm_iteration& it) {
+  if (s->n_trace < kTraceMax) trace[s->n_trace] = it;
   s->n_trace++;
 }
 
-CLC_HD void lm_init(LmState* s, const double* pose7, const clc_lm_options& opt) {
+CLC_HD void lm_init(LmCore* s, const double* pose7, const clc_lm_options& opt) {
   s->done = 0; s->phase = 0; s->iteration = 0; s->num_invalid = 0; s->reuse_diagonal = 0; s->n_trace = 0;
   s->num_successful = 0; s->num_unsuccessful = 0; s->sweeps = 0; s->pad0 = 0;
   for (int i = 0; i < 7; ++i) { s->x[i] = pose7[i]; s->cand[i] = pose7[i]; }
@@ -80,7 +88,7 @@ CLC_HD void lm_init(LmState* s, const double* pose7, const clc_lm_options& opt) 
 
 // Consumes the 28 sums of the sweep that has just evaluated s->cand and advances the minimiser until it either
 // terminates (s->done != 0) or has a new candidate in s->cand for the next sweep.
-CLC_HD void lm_update(LmState* s, const double* sums) {
+CLC_HD void lm_update(LmCore* s, clc_lm_iteration* trace, const double* sums) {
   if (s->done) return;
   s->sweeps++;
   const clc_lm_options& o = s->opt;
@@ -114,13 +122,13 @@ CLC_HD void lm_update(LmState* s, const double* sums) {
     // Ceres: ParameterToleranceReached
     if (last.step_norm <= o.parameter_tolerance * (s->x_norm + o.parameter_tolerance)) {
       s->done = CLC_TERM_CONVERGENCE_PARAMETER;
-      lm_record(s, last);
+      lm_record(s, trace, last);
       return;
     }
     // Ceres: FunctionToleranceReached (tested before the accept/reject decision; the candidate is not applied)
     if (fabs(last.cost_change) <= o.function_tolerance * s->x_cost) {
       s->done = CLC_TERM_CONVERGENCE_FUNCTION;
-      lm_record(s, last);
+      lm_record(s, trace, last);
       return;
     }
     last.relative_decrease = last.cost_change / s->model_cost_change;
@@ -152,7 +160,7 @@ CLC_HD void lm_update(LmState* s, const double* sums) {
     // ---- Ceres: FinalizeIterationAndCheckIfMinimizerCanContinue ----
     if (last.step_is_successful) s->num_successful++; else s->num_unsuccessful++;
     last.trust_region_radius = s->radius;
-    lm_record(s, last);
+    lm_record(s, trace, last);
     s->iteration = last.iteration;
     if (last.iteration >= o.max_num_iterations) { s->done = CLC_TERM_NO_CONVERGENCE; return; }
     if (last.step_is_successful && last.gradient_max_norm <= o.gradient_tolerance) {

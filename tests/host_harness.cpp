@@ -10,15 +10,18 @@ extern "C" {
 
 int harness_lm_state_size() { return (int)sizeof(clc::LmState); }
 void harness_lm_init(void* st, const double* pose7, const clc_lm_options* opt) {
-  clc::lm_init(static_cast<clc::LmState*>(st), pose7, *opt);
+  clc::lm_init(&static_cast<clc::LmState*>(st)->core, pose7, *opt);
 }
-void harness_lm_update(void* st, const double* sums28) { clc::lm_update(static_cast<clc::LmState*>(st), sums28); }
-int harness_lm_done(const void* st) { return static_cast<const clc::LmState*>(st)->done; }
-int harness_lm_ntrace(const void* st) { return static_cast<const clc::LmState*>(st)->n_trace; }
-void harness_lm_cand(const void* st, double* out) { std::memcpy(out, static_cast<const clc::LmState*>(st)->cand, 56); }
-void harness_lm_x(const void* st, double* out) { std::memcpy(out, static_cast<const clc::LmState*>(st)->x, 56); }
+void harness_lm_update(void* st, const double* sums28) {
+  clc::LmState* s = static_cast<clc::LmState*>(st);
+  clc::lm_update(&s->core, s->trace, sums28);
+}
+int harness_lm_done(const void* st) { return static_cast<const clc::LmState*>(st)->core.done; }
+int harness_lm_ntrace(const void* st) { return static_cast<const clc::LmState*>(st)->core.n_trace; }
+void harness_lm_cand(const void* st, double* out) { std::memcpy(out, static_cast<const clc::LmState*>(st)->core.cand, 56); }
+void harness_lm_x(const void* st, double* out) { std::memcpy(out, static_cast<const clc::LmState*>(st)->core.x, 56); }
 void harness_lm_trace(const void* st, int i, clc_lm_iteration* out) { *out = static_cast<const clc::LmState*>(st)->trace[i]; }
-int harness_lm_sweeps(const void* st) { return static_cast<const clc::LmState*>(st)->sweeps; }
+int harness_lm_sweeps(const void* st) { return static_cast<const clc::LmState*>(st)->core.sweeps; }
 
 // moments of one piece (computed by the caller) -> the 28 sums, through the same code path as the kernel
 void harness_expand_lm(const double* plane, const double* pose7, double count, const double* S10, int use_loss,
