@@ -134,6 +134,11 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   return v;
 }
 
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 // gpu-scope acq_rel fetch-add: releases this block's partial sums (ordered before it by the preceding block barrier)
 // and acquires the other blocks' when it turns out to be the last ticket
 __device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
@@ -257,7 +262,6 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
   __shared__ double s_acc[kWarps][NOUT];
   __shared__ double s_red[kWarps][32];
-  __shared__ bool s_last;
 
   if (args.done != nullptr && *args.done != 0) return;
   CLC_STAMP(0);
@@ -526,14 +530,19 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   }
   __syncthreads();
   CLC_STAMP(3);
+  // Every block releases its partial sums with a ticket.  The final reduction (and the LM update) always runs on block 0
+  // -- the persistent grid is fully co-resident, so block 0 can wait for the other tickets -- rather than on whichever
+  // block happens to finish last: the ~1000 instructions of that serial tail then stay warm in ONE SM's instruction
+  // cache from launch to launch instead of being fetched cold from L2 by a different SM every time.
+  if (threadIdx.x == 0) atom_add_acq_rel_gpu(args.ticket, 1u);
+  if (blockIdx.x != 0) return;
   if (threadIdx.x == 0) {
-    const unsigned int t = atom_add_acq_rel_gpu(args.ticket, 1u);
-    s_last = (t == gridDim.x - 1);
+    while (ld_acquire_gpu(args.ticket) != gridDim.x) {
+    }
   }
   __syncthreads();
-  if (!s_last) return;
 
-  // ---- last block: deterministic sum of the block partials ----
+  // ---- block 0: deterministic sum of the block partials ----
   {
     // warp wv sums blocks wv, wv+8, ...; lane handles output `lane` (and lane+32 for the 54-wide mode).  The loads
     // of a round are independent L2 round trips issued back to back; the additions keep the block order.

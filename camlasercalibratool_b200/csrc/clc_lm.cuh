@@ -171,8 +171,10 @@ CLC_HD void lm_update(LmCore* s, clc_lm_iteration* trace, const double* sums) {
 
     // ---- Ceres: LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system ----
     double Hs[36], gs[6], A[36], step[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) {
       gs[i] = s->scale[i] * s->g[i];
+#pragma unroll
       for (int j = i; j < 6; ++j) {
         const double v = s->scale[i] * s->scale[j] * s->H[tri(i, j)];
         Hs[i * 6 + j] = v;
@@ -180,16 +182,21 @@ CLC_HD void lm_update(LmCore* s, clc_lm_iteration* trace, const double* sums) {
       }
     }
     if (!s->reuse_diagonal)
+#pragma unroll
       for (int k = 0; k < 6; ++k) {
         double dd = Hs[k * 6 + k];
         dd = dd > o.min_lm_diagonal ? dd : o.min_lm_diagonal;
         dd = dd < o.max_lm_diagonal ? dd : o.max_lm_diagonal;
         s->diag[k] = dd;
       }
+#pragma unroll
     for (int i = 0; i < 36; ++i) A[i] = Hs[i];
-    for (int k = 0; k < 6; ++k) A[k * 6 + k] += s->diag[k] / s->radius;  // D^2 = diag / radius
+    const double inv_radius = 1.0 / s->radius;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) A[k * 6 + k] += s->diag[k] * inv_radius;  // D^2 = diag / radius
     bool ok = chol6_solve(A, gs, step);
     s->reuse_diagonal = 1;
+#pragma unroll
     for (int k = 0; k < 6; ++k) {
       if (!is_finite(step[k])) ok = false;
       step[k] = -step[k];
@@ -198,9 +205,11 @@ CLC_HD void lm_update(LmCore* s, clc_lm_iteration* trace, const double* sums) {
     double mcc = 0.0;
     if (ok) {
       double gs_s = 0.0, sHs = 0.0;
+#pragma unroll
       for (int i = 0; i < 6; ++i) {
         gs_s += gs[i] * step[i];
         double r = 0.0;
+#pragma unroll
         for (int j = 0; j < 6; ++j) r += Hs[i * 6 + j] * step[j];
         sHs += step[i] * r;
       }

@@ -257,32 +257,42 @@ CLC_HD int tri(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }  //
 
 // Cholesky solve of the SPD 6x6 system A y = b (A full row-major).  false if not positive definite.
 CLC_HD bool chol6_solve(const double* A, const double* b, double* y) {
-  // deliberately compact (rolled loops): this runs once per sweep on one thread from a cold instruction cache
-  double L[36];
+  // fully unrolled (L, z, inv live in registers): it always runs on the same SM (block 0), whose instruction cache keeps it.
+  // One reciprocal per pivot instead of one division per entry (divisions are ~100-cycle subroutines in FP64).
+  double L[36], inv[6];
   bool ok = true;
-  for (int i = 0; i < 6; ++i) {
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i * 6 + j];
-      for (int k = 0; k < j; ++k) s -= L[i * 6 + k] * L[j * 6 + k];
-      if (i == j) {
-        ok = ok && (s > 0.0);
-        L[i * 6 + i] = sqrt(s);
-      } else {
-        L[i * 6 + j] = s / L[j * 6 + j];
-      }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double s = A[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s -= L[j * 6 + k] * L[j * 6 + k];
+    ok = ok && (s > 0.0);
+    const double d = sqrt(s);
+    L[j * 6 + j] = d;
+    inv[j] = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double t = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t -= L[i * 6 + k] * L[j * 6 + k];
+      L[i * 6 + j] = t * inv[j];
     }
   }
   if (!ok) return false;
   double z[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
+#pragma unroll
     for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * z[k];
-    z[i] = s / L[i * 6 + i];
+    z[i] = s * inv[i];
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double s = z[i];
+#pragma unroll
     for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * y[k];
-    y[i] = s / L[i * 6 + i];
+    y[i] = s * inv[i];
   }
   return true;
 }
