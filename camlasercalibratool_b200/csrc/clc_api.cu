@@ -248,6 +248,7 @@ struct clc_problem {
   double* flush_buf = nullptr;
   int64_t flush_n = 0;
   unsigned long long* timing = nullptr;  // profiling hook (clc_debug_sweep_timing)
+  bool use_pdl = true;                   // CLC_PDL=0 disables programmatic dependent launch in the LM loop
   // pinned host mirrors (views into one pooled block)
   PinnedBlock* pinned = nullptr;
   double* h_sums = nullptr;
@@ -289,7 +290,7 @@ int set_device(const clc_problem* p) {
 // one K1 launch on the problem's stream
 // collective: the sums of this launch are to be all-reduced (in-kernel when the peer path is active)
 int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* d_pose, const int* d_done,
-                 clc::LmState* d_lm, bool collective = true) {
+                 clc::LmState* d_lm, bool collective = true, bool pdl = false) {
   clc::SweepArgs a;
   a.pose7 = d_pose;
   a.done = d_done;
@@ -312,13 +313,26 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
     for (int r = 0; r < c->nranks; ++r) a.peer_mailbox[r] = static_cast<unsigned long long*>(c->peer_block[r]);
   }
   const clc::ProblemView v = make_view(p);
+  // cudaLaunchKernelEx so that back-to-back sweeps of the LM loop can use programmatic dependent launch
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)p->grid);
+  cfg.blockDim = dim3(clc::kThreads);
+  cfg.dynamicSmemBytes = clc::kDynSmemBytes;
+  cfg.stream = p->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le;
   if (mode == clc::kModeClosedForm) {
-    clc::clc_sweep_kernel<false, clc::kModeClosedForm><<<p->grid, clc::kThreads, clc::kDynSmemBytes, p->stream>>>(v, a);
+    le = cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeClosedForm>, v, a);
   } else if (loss) {
-    clc::clc_sweep_kernel<true, clc::kModeLM><<<p->grid, clc::kThreads, clc::kDynSmemBytes, p->stream>>>(v, a);
+    le = cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM>, v, a);
   } else {
-    clc::clc_sweep_kernel<false, clc::kModeLM><<<p->grid, clc::kThreads, clc::kDynSmemBytes, p->stream>>>(v, a);
+    le = cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeLM>, v, a);
   }
+  if (le != cudaSuccess) return fail(CLC_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(le));
   CLC_LAUNCH_CHECK();
   return CLC_OK;
 }
@@ -364,6 +378,7 @@ int finish_create(clc_problem* p) {
     if (v >= 1) blocks_per_sm = std::min(v, std::max(1, occ_min));
   }
   p->grid = p->num_sms * blocks_per_sm;
+  if (const char* env = std::getenv("CLC_PDL")) p->use_pdl = std::atoi(env) != 0;
   const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
   p->per_warp = std::max<int64_t>(clc::kChunk, round_up((p->n_points + n_warps - 1) / n_warps, clc::kChunk));
   CLC_CUDA(cudaMallocAsync(&p->warp_first_frame, sizeof(int) * n_warps, p->stream));
@@ -784,7 +799,10 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
   while (launched < max_sweeps) {
     const int batch = std::min(opt.iterations_per_sync, max_sweeps - launched);
     for (int i = 0; i < batch; ++i) {
-      rc = launch_sweep(p, clc::kModeLM, loss, edges, p->lm->core.cand, &p->lm->core.done, fused_update ? p->lm : nullptr);
+      // fused mode: one kernel per LM iteration, chained with programmatic dependent launch (the next sweep prefetches
+      // its first stages while this one's block 0 reduces and updates)
+      rc = launch_sweep(p, clc::kModeLM, loss, edges, p->lm->core.cand, &p->lm->core.done, fused_update ? p->lm : nullptr,
+                        /*collective=*/true, /*pdl=*/fused_update && p->use_pdl);
       if (rc != CLC_OK) return rc;
       if (!fused_update) {
         rc = allreduce_sums(p, clc::kNumSums);

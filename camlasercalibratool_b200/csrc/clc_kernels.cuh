@@ -263,7 +263,6 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   __shared__ double s_acc[kWarps][NOUT];
   __shared__ double s_red[kWarps][32];
 
-  if (args.done != nullptr && *args.done != 0) return;
   CLC_STAMP(0);
   if (args.timing != nullptr && threadIdx.x == 0) {
     unsigned int smid;
@@ -303,6 +302,17 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     for (int c = 0; c < kStages && c < n_chunks; ++c) issue_chunk(c);
   }
   __syncwarp();
+
+  // Programmatic dependent launch: everything above touched only constant data (the points), so it overlaps the
+  // tail of the previous sweep (final reduce + LM update on its block 0).  From here on the pose, the `done` flag,
+  // the partial sums and the ticket of the previous launch are needed: wait for it to complete.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (args.done != nullptr && *args.done != 0) {
+    // the LM finished: nothing to do, but the bulk copies already in flight must land before the block may exit
+    const int issued = n_chunks < kStages ? n_chunks : kStages;
+    for (int c = 0; c < issued; ++c) mbar_wait(bars + c, 0u);
+    return;
+  }
 
   for (int k = lane; k < NOUT; k += 32) s_acc[warp][k] = 0.0;
 
@@ -535,6 +545,8 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   // block happens to finish last: the ~1000 instructions of that serial tail then stay warm in ONE SM's instruction
   // cache from launch to launch instead of being fetched cold from L2 by a different SM every time.
   if (threadIdx.x == 0) atom_add_acq_rel_gpu(args.ticket, 1u);
+  // let the next sweep's blocks be scheduled on the SMs this grid is vacating (they only prefetch until we complete)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (blockIdx.x != 0) return;
   if (threadIdx.x == 0) {
     while (ld_acquire_gpu(args.ticket) != gridDim.x) {
