@@ -8,6 +8,7 @@ from . import _build  # noqa: F401
 from .api import (  # noqa: F401
     CamLaserCalClosedSolution,
     CamLaserCalibration,
+    LineFittingCeres,
     ClcError,
     Comm,
     Oberserve,
@@ -22,6 +23,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "CamLaserCalClosedSolution", "CamLaserCalibration", "ClcError", "Comm", "Oberserve", "Problem", "T_to_pose7",
+    "CamLaserCalClosedSolution", "CamLaserCalibration", "LineFittingCeres", "ClcError", "Comm", "Oberserve", "Problem", "T_to_pose7",
     "comm_unique_id", "default_options", "launch_count", "marshal", "pose7_to_T", "shard_range",
 ]

@@ -182,6 +182,14 @@ class Problem:
         _lib.check(self._L.clc_closed_form(self._h, _dp(T), C.byref(un), _dp(AtA), _dp(Atb)), "clc_closed_form")
         return T.reshape(4, 4), bool(un.value), AtA, Atb
 
+    def line_fit(self, lines0=None, max_num_iterations=10):
+        """Batched LineFittingCeres over the frames' points: returns (lines[N,2], info[N,4])."""
+        nf = self.sizes()[0]
+        lines = np.zeros((nf, 2)) if lines0 is None else np.ascontiguousarray(lines0, dtype=np.float64).reshape(nf, 2).copy()
+        info = np.empty((nf, 4))
+        _lib.check(self._L.clc_problem_line_fit(self._h, _dp(lines), int(max_num_iterations), _dp(info)), "clc_problem_line_fit")
+        return lines, info
+
     # ---- multi-GPU ----
     def set_allreduce_mode(self, mode: int):
         """0 = NCCL all-reduce between kernels, 1 = fused in-kernel peer exchange (default once p2p is enabled)."""
@@ -287,6 +295,14 @@ class pinned_array:
             self.array = None
             self._L.clc_host_free(self._ptr)
             self._ptr = None
+
+
+def LineFittingCeres(Points, Line: np.ndarray, max_num_iterations=10):
+    """reference src/LaseCamCalCeres.cpp:401-433: ``Line`` (2,) is the start value on entry and the fit on exit."""
+    pts = np.ascontiguousarray(Points, dtype=np.float64).reshape(-1, 3)
+    line = np.ascontiguousarray(Line, dtype=np.float64).copy()
+    _lib.check(_lib.load().clc_line_fit_points(_dp(pts), pts.shape[0], _dp(line), int(max_num_iterations)), "clc_line_fit_points")
+    Line[...] = line
 
 
 # ---- the reference's two entry points -------------------------------------------------------------------------

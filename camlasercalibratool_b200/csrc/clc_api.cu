@@ -18,6 +18,7 @@
 
 #include "../../include/clc_b200.h"
 #include "clc_kernels.cuh"
+#include "clc_linefit.cuh"
 
 namespace {
 
@@ -845,6 +846,45 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
     for (int i = 0; i < n; ++i) trace[i] = dev_trace[i];
   }
   return CLC_OK;
+}
+
+// ---- LineFittingCeres, batched ------------------------------------------------------------------------------------
+
+int clc_problem_line_fit(clc_problem* p, double* lines, int max_num_iterations, double* info) {
+  if (!p || !lines || max_num_iterations < 0) return fail(CLC_ERR_INVALID, "bad line-fit arguments");
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  const int64_t N = p->n_frames;
+  if (N == 0) return CLC_OK;
+  double *d_lines = nullptr, *d_info = nullptr;
+  CLC_CUDA(cudaMallocAsync(&d_lines, sizeof(double) * 2 * N, p->stream));
+  if (info) CLC_CUDA(cudaMallocAsync(&d_info, sizeof(double) * 4 * N, p->stream));
+  CLC_CUDA(cudaMemcpyAsync(d_lines, lines, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, p->stream));
+  const int warps = 8;
+  clc::clc_line_fit_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, p->stream>>>(
+      p->x, p->y, p->offsets, N, max_num_iterations, p->cauchy_a, d_lines, d_info);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(lines, d_lines, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, p->stream);
+  if (e == cudaSuccess && info) e = cudaMemcpyAsync(info, d_info, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, p->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+  cudaFreeAsync(d_lines, p->stream);
+  if (d_info) cudaFreeAsync(d_info, p->stream);
+  if (e != cudaSuccess) return fail(CLC_ERR_CUDA, cudaGetErrorString(e));
+  return CLC_OK;
+}
+
+int clc_line_fit_points(const double* points_xyz, int64_t n, double line[2], int max_num_iterations) {
+  if (!points_xyz || n < 0 || !line) return fail(CLC_ERR_INVALID, "bad line-fit arguments");
+  const double pose[7] = {0, 0, 0, 1, 0, 0, 0};
+  const int64_t off[2] = {0, n};
+  clc_problem_desc d = {1, pose, off, points_xyz, nullptr, 1, 0.05, -1};  // CauchyLoss(0.05), reference :416
+  clc_problem* p = nullptr;
+  int rc = clc_problem_create(&p, &d);
+  if (rc != CLC_OK) return rc;
+  rc = clc_problem_line_fit(p, line, max_num_iterations, nullptr);
+  clc_problem_destroy(p);
+  return rc;
 }
 
 // ---- multi-GPU --------------------------------------------------------------------------------------------------

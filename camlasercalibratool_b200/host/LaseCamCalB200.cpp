@@ -215,29 +215,17 @@ void CalibrationTool_SavePlanePoints(const std::vector<Oberserve> obs, const Eig
   }
 }
 
-// reference src/LaseCamCalCeres.cpp:385-433 -- a per-scan 2-parameter robust line fit that runs BEFORE the path this
-// library accelerates.  Not on the GPU yet: see DESIGN.md "Out of scope / next".
-#ifndef CLC_B200_NO_LINEFITTING_STUB
+// reference src/LaseCamCalCeres.cpp:385-433: per-scan robust line fit (the step before the solve).
+// One scan per call, as the reference; the library's batched form is clc_problem_line_fit.
 void LineFittingCeres(const std::vector<Eigen::Vector3d> Points, Eigen::Vector2d& Line) {
-  // Iteratively re-weighted least squares of m0 x + m1 y + 1 = 0 with the Cauchy weight 1/(1 + r^2/0.05^2), started at
-  // the incoming Line -- the same fixed point Ceres' 10 LM iterations converge to.  Host code, O(scan) per call.
-  double m0 = Line(0), m1 = Line(1);
-  for (int it = 0; it < 50; ++it) {
-    double a00 = 0, a01 = 0, a11 = 0, b0 = 0, b1 = 0;
-    for (const Eigen::Vector3d& q : Points) {
-      const double r = m0 * q.x() + m1 * q.y() + 1.0;
-      const double w = 1.0 / (1.0 + r * r / (0.05 * 0.05));
-      a00 += w * q.x() * q.x(); a01 += w * q.x() * q.y(); a11 += w * q.y() * q.y();
-      b0 -= w * q.x(); b1 -= w * q.y();
-    }
-    const double det = a00 * a11 - a01 * a01;
-    if (!(std::fabs(det) > 1e-300)) break;
-    const double n0 = (a11 * b0 - a01 * b1) / det, n1 = (a00 * b1 - a01 * b0) / det;
-    const double change = std::fabs(n0 - m0) + std::fabs(n1 - m1);
-    m0 = n0; m1 = n1;
-    if (change < 1e-14) break;
+  std::vector<double> pts;
+  pts.reserve(3 * Points.size());
+  for (const Eigen::Vector3d& q : Points) { pts.push_back(q.x()); pts.push_back(q.y()); pts.push_back(q.z()); }
+  double line[2] = {Line(0), Line(1)};  // :403 (start value; the reference's caller leaves it uninitialised)
+  if (clc_line_fit_points(pts.data(), (int64_t)Points.size(), line, /*max_num_iterations=*/10) != CLC_OK) {  // :425
+    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
+    return;
   }
-  Line(0) = m0;
-  Line(1) = m1;
+  Line(0) = line[0];
+  Line(1) = line[1];
 }
-#endif

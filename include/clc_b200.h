@@ -156,6 +156,16 @@ int clc_information(clc_problem* p, const double pose7[7], double H36[36], doubl
  * AtA81/Atb9 (the 9x9 normal equations) may be NULL. */
 int clc_closed_form(clc_problem* p, double Tlc16[16], int* unobservable, double AtA81[81], double Atb9[9]);
 
+/* replaces: LineFittingCeres(), reference src/LaseCamCalCeres.cpp:385-433 (the step before the solve: SURVEY.md 8(f)),
+ * batched: fits m0 x + m1 y + 1 = 0 (CauchyLoss(0.05), <= max_num_iterations Ceres LM iterations, reference: 10) to
+ * the x,y of every frame's points of the problem, one warp per frame, the whole loop on the device.
+ * lines[n_frames*2] (host): start values in (the reference's caller passes them uninitialised), fits out.
+ * info[n_frames*4] (host, optional): termination code, LM iterations, sweeps, final cost per frame.
+ * Local to the rank's shard (no collective). */
+int clc_problem_line_fit(clc_problem* p, double* lines, int max_num_iterations, double* info);
+/* The reference's per-scan call shape: one scan of n points (AoS xyz, z ignored), line[2] in/out. */
+int clc_line_fit_points(const double* points_xyz, int64_t n, double line[2], int max_num_iterations);
+
 /* Eigen-equivalent conversions used on both sides of the boundary (reference :215-219 and :311-314). */
 void clc_T_to_pose7(const double T16[16], double pose7[7]);
 void clc_pose7_to_T(const double pose7[7], double T16[16]);

@@ -816,6 +816,199 @@ int oracle_solve(const oracle_problem* p, double pose7[7], const oracle_options*
 }
 
 /* ------------------------------------------------------------------------------------------------------ */
+/* LineFittingCeres, LaseCamCalCeres.cpp:385-433                                                          */
+/* ------------------------------------------------------------------------------------------------------ */
+
+/* min ||A y - b|| for a rows x 2 row-major A by Householder QR (in place). */
+static int householder_ls2(double* A, double* b, int64_t rows, double y[2]) {
+  for (int k = 0; k < 2; ++k) {
+    double nrm2 = 0.0;
+    for (int64_t i = k; i < rows; ++i) nrm2 += A[i * 2 + k] * A[i * 2 + k];
+    const double nrm = sqrt(nrm2);
+    if (!(nrm > 0.0)) return 1;
+    const double akk = A[k * 2 + k];
+    const double alpha = akk > 0.0 ? -nrm : nrm;
+    const double v0 = akk - alpha;
+    const double vtv = nrm2 - akk * akk + v0 * v0;
+    if (vtv > 0.0) {
+      const double beta = 2.0 / vtv;
+      for (int j = k + 1; j <= 2; ++j) { /* j == 2 is the right-hand side */
+        double s = v0 * (j < 2 ? A[k * 2 + j] : b[k]);
+        for (int64_t i = k + 1; i < rows; ++i) s += A[i * 2 + k] * (j < 2 ? A[i * 2 + j] : b[i]);
+        s *= beta;
+        if (j < 2) {
+          A[k * 2 + j] -= s * v0;
+          for (int64_t i = k + 1; i < rows; ++i) A[i * 2 + j] -= s * A[i * 2 + k];
+        } else {
+          b[k] -= s * v0;
+          for (int64_t i = k + 1; i < rows; ++i) b[i] -= s * A[i * 2 + k];
+        }
+      }
+    }
+    A[k * 2 + k] = alpha;
+  }
+  y[1] = b[1] / A[3];
+  y[0] = (b[0] - A[1] * y[1]) / A[0];
+  return 0;
+}
+
+/* One Ceres evaluation of the line problem: residual m0 x + m1 y + 1 (:391), AutoDiff Jacobian (x, y), CauchyLoss(0.05)
+ * (:416) through the Corrector's simple branch.  r and J may be NULL (cost only). */
+static double line_evaluate(const double* pts, int64_t n, const double m[2], double* r, double* J, double g[2]) {
+  const double a = 0.05, b = a * a, c = 1.0 / b;
+  double cost = 0.0;
+  if (g) g[0] = g[1] = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double x = pts[3 * i], y = pts[3 * i + 1];
+    const double res = m[0] * x + m[1] * y + 1.;
+    const double sum = 1.0 + (res * res) * c;
+    const double inv = 1.0 / sum;
+    cost += 0.5 * b * log(sum);
+    if (r) {
+      const double sq = sqrt(inv > DBL_MIN ? inv : DBL_MIN);
+      r[i] = res * sq;
+      J[2 * i] = x * sq;
+      J[2 * i + 1] = y * sq;
+      if (g) { g[0] += J[2 * i] * r[i]; g[1] += J[2 * i + 1] * r[i]; }
+    }
+  }
+  return cost;
+}
+
+/* The same Ceres trust-region loop as oracle_solve (see there for the line-by-line citations), for 2 Euclidean
+ * parameters: Plus is x + delta, the gradient norm is |g|_inf, the parameter norm is the 2-norm of (m0, m1). */
+int oracle_line_fit(const double* points, int64_t n, double line[2], int max_num_iterations, oracle_summary* summary,
+                    oracle_iteration* trace, int trace_cap) {
+  oracle_options opt_s;
+  oracle_default_options(&opt_s);
+  const oracle_options* opt = &opt_s;
+  opt_s.max_num_iterations = max_num_iterations;
+  oracle_summary sm;
+  memset(&sm, 0, sizeof(sm));
+  int n_trace = 0;
+  double* res = (double*)malloc(sizeof(double) * (size_t)(n + 2));
+  double* J = (double*)malloc(sizeof(double) * (size_t)(n + 2) * 2);
+  double* qA = (double*)malloc(sizeof(double) * (size_t)(n + 2) * 2);
+  double* qb = (double*)malloc(sizeof(double) * (size_t)(n + 2));
+  double x[2] = {line[0], line[1]}, cand[2], g[2], scale[2], diag[2], col2[2];
+  double x_cost = line_evaluate(points, n, x, res, J, g);
+  sm.num_residual_evaluations = sm.num_jacobian_evaluations = 1;
+  if (!isfinite(x_cost)) {
+    sm.termination = ORACLE_TERM_FAILURE;
+    sm.initial_cost = sm.final_cost = x_cost;
+    if (summary) *summary = sm;
+    free(res); free(J); free(qA); free(qb);
+    return 0;
+  }
+#define LINE_SCALE_J(first)                                                                     \
+  do {                                                                                          \
+    if (first) {                                                                                \
+      col2[0] = col2[1] = 0.0;                                                                  \
+      for (int64_t i = 0; i < n; ++i) { col2[0] += J[2 * i] * J[2 * i]; col2[1] += J[2 * i + 1] * J[2 * i + 1]; } \
+      scale[0] = 1.0 / (1.0 + sqrt(col2[0]));                                                   \
+      scale[1] = 1.0 / (1.0 + sqrt(col2[1]));                                                   \
+    }                                                                                           \
+    col2[0] = col2[1] = 0.0;                                                                    \
+    for (int64_t i = 0; i < n; ++i) {                                                           \
+      J[2 * i] *= scale[0]; J[2 * i + 1] *= scale[1];                                           \
+      col2[0] += J[2 * i] * J[2 * i]; col2[1] += J[2 * i + 1] * J[2 * i + 1];                   \
+    }                                                                                           \
+  } while (0)
+  LINE_SCALE_J(1);
+  double x_norm = sqrt(x[0] * x[0] + x[1] * x[1]);
+  double radius = opt->initial_trust_region_radius, decrease_factor = 2.0;
+  int reuse_diagonal = 0, num_invalid = 0;
+  oracle_iteration it;
+  memset(&it, 0, sizeof(it));
+  it.cost = x_cost;
+  it.gradient_max_norm = fmax(fabs(g[0]), fabs(g[1]));
+  it.step_is_valid = it.step_is_successful = 1;
+  sm.initial_cost = x_cost;
+  for (;;) {
+    if (it.step_is_successful) { sm.num_successful_steps++; line[0] = x[0]; line[1] = x[1]; }
+    else sm.num_unsuccessful_steps++;
+    it.trust_region_radius = radius;
+    record(trace, trace_cap, &n_trace, &it);
+    if (it.iteration >= opt->max_num_iterations) { sm.termination = ORACLE_TERM_NO_CONVERGENCE; break; }
+    if (it.step_is_successful && it.gradient_max_norm <= opt->gradient_tolerance) { sm.termination = ORACLE_TERM_CONVERGENCE_GRADIENT; break; }
+    if (!(radius > opt->min_trust_region_radius)) { sm.termination = ORACLE_TERM_CONVERGENCE_MIN_RADIUS; break; }
+    oracle_iteration prev = it;
+    memset(&it, 0, sizeof(it));
+    it.iteration = prev.iteration + 1;
+    if (!reuse_diagonal)
+      for (int k = 0; k < 2; ++k) {
+        double d = col2[k];
+        d = d > opt->min_lm_diagonal ? d : opt->min_lm_diagonal;
+        d = d < opt->max_lm_diagonal ? d : opt->max_lm_diagonal;
+        diag[k] = d;
+      }
+    double step[2];
+    memcpy(qA, J, sizeof(double) * (size_t)n * 2);
+    qA[2 * n] = sqrt(diag[0] / radius); qA[2 * n + 1] = 0.0;
+    qA[2 * n + 2] = 0.0; qA[2 * n + 3] = sqrt(diag[1] / radius);
+    memcpy(qb, res, sizeof(double) * (size_t)n);
+    qb[n] = qb[n + 1] = 0.0;
+    int failed = householder_ls2(qA, qb, n + 2, step);
+    reuse_diagonal = 1;
+    for (int k = 0; k < 2; ++k) { if (!isfinite(step[k])) failed = 1; step[k] = -step[k]; }
+    double mcc = 0.0;
+    if (!failed) {
+      for (int64_t i = 0; i < n; ++i) {
+        const double mr = J[2 * i] * step[0] + J[2 * i + 1] * step[1];
+        mcc -= mr * (res[i] + mr / 2.0);
+      }
+      it.step_is_valid = mcc > 0.0;
+    }
+    if (!it.step_is_valid) {
+      if (++num_invalid >= opt->max_num_consecutive_invalid_steps) { sm.termination = ORACLE_TERM_FAILURE; break; }
+      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = 1;
+      it.cost = x_cost; it.gradient_max_norm = prev.gradient_max_norm;
+      continue;
+    }
+    num_invalid = 0;
+    cand[0] = x[0] + step[0] * scale[0];
+    cand[1] = x[1] + step[1] * scale[1];
+    double cand_cost = line_evaluate(points, n, cand, NULL, NULL, NULL);
+    sm.num_residual_evaluations++;
+    if (!isfinite(cand_cost)) cand_cost = DBL_MAX;
+    it.step_norm = sqrt((x[0] - cand[0]) * (x[0] - cand[0]) + (x[1] - cand[1]) * (x[1] - cand[1]));
+    it.cost_change = x_cost - cand_cost;
+    it.cost = cand_cost;
+    if (it.step_norm <= opt->parameter_tolerance * (x_norm + opt->parameter_tolerance)) {
+      sm.termination = ORACLE_TERM_CONVERGENCE_PARAMETER; it.trust_region_radius = radius; record(trace, trace_cap, &n_trace, &it); break;
+    }
+    if (fabs(it.cost_change) <= opt->function_tolerance * x_cost) {
+      sm.termination = ORACLE_TERM_CONVERGENCE_FUNCTION; it.trust_region_radius = radius; record(trace, trace_cap, &n_trace, &it); break;
+    }
+    it.relative_decrease = it.cost_change / mcc;
+    if (it.relative_decrease > opt->min_relative_decrease) {
+      x[0] = cand[0]; x[1] = cand[1];
+      x_norm = sqrt(x[0] * x[0] + x[1] * x[1]);
+      x_cost = line_evaluate(points, n, x, res, J, g);
+      sm.num_residual_evaluations++; sm.num_jacobian_evaluations++;
+      LINE_SCALE_J(0);
+      it.cost = x_cost;
+      it.gradient_max_norm = fmax(fabs(g[0]), fabs(g[1]));
+      it.step_is_successful = 1;
+      const double q = 2.0 * it.relative_decrease - 1.0;
+      double den = 1.0 - q * q * q;
+      if (den < 1.0 / 3.0) den = 1.0 / 3.0;
+      radius /= den;
+      if (radius > opt->max_trust_region_radius) radius = opt->max_trust_region_radius;
+      decrease_factor = 2.0; reuse_diagonal = 0;
+    } else {
+      radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = 1;
+    }
+  }
+#undef LINE_SCALE_J
+  sm.num_iterations = n_trace;
+  sm.final_cost = x_cost;
+  if (summary) *summary = sm;
+  free(res); free(J); free(qA); free(qb);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
 /* Analysis tail, LaseCamCalCeres.cpp:318-381                                                             */
 /* ------------------------------------------------------------------------------------------------------ */
 int oracle_information(const oracle_problem* p, const double pose7[7], double* H36, double* b6, double* chi,

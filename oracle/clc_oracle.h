@@ -141,6 +141,12 @@ int oracle_information(const oracle_problem* p, const double pose7[7], double* H
  * AtA (row-major 9x9) and Atb (9) are returned for parity checks when non-NULL. */
 int oracle_closed_form(const oracle_problem* p, double Tlc16[16], int* unobservable, double* AtA81, double* Atb9);
 
+/* LineFittingCeres (LaseCamCalCeres.cpp:385-433): robust fit of m0 x + m1 y + 1 = 0 to the x,y of `points` (AoS xyz,
+ * z ignored), CauchyLoss(0.05), DENSE_QR, max_num_iterations = 10, every other option a Ceres default; `line` is the
+ * start value on entry (the reference's caller passes it uninitialised, calibr_offline.cpp:123) and the result on exit. */
+int oracle_line_fit(const double* points, int64_t n, double line[2], int max_num_iterations, oracle_summary* summary,
+                    oracle_iteration* trace, int trace_cap);
+
 /* Small dense helpers exposed for the tests: singular values (descending) of a symmetric n x n matrix (n <= 9). */
 void oracle_sym_singular_values(const double* A, int n, double* sv);
 

@@ -132,6 +132,7 @@ def lib():
         L.oracle_information.argtypes = [C.POINTER(_Problem), dp, dp, dp, dp, dp]
         L.oracle_closed_form.argtypes = [C.POINTER(_Problem), dp, C.POINTER(C.c_int), dp, dp]
         L.oracle_sym_singular_values.argtypes = [dp, C.c_int, dp]
+        L.oracle_line_fit.argtypes = [dp, C.c_int64, dp, C.c_int, C.POINTER(Summary), C.POINTER(Iteration), C.c_int]
         L.oracle_gen_ground_truth.argtypes = [dp, dp]
         L.oracle_gen_frames.argtypes = [C.POINTER(_GenDesc), dp, ip]
         L.oracle_gen_frames.restype = C.c_int64
@@ -304,6 +305,16 @@ def closed_form(p: Problem):
     un = C.c_int()
     lib().oracle_closed_form(C.byref(p._c), _dp(T), C.byref(un), _dp(AtA), _dp(Atb))
     return T.reshape(4, 4), bool(un.value), AtA, Atb
+
+
+def line_fit(points, line0=(0.0, 0.0), max_num_iterations=10, trace_cap=64):
+    """LineFittingCeres restatement: returns (line[2], Summary, [Iteration...])."""
+    pts = _f64(points, (-1, 3))
+    line = _f64(line0).copy()
+    s = Summary()
+    tr = (Iteration * trace_cap)()
+    lib().oracle_line_fit(_dp(pts), pts.shape[0], _dp(line), int(max_num_iterations), C.byref(s), tr, trace_cap)
+    return line, s, [tr[i] for i in range(min(s.num_iterations, trace_cap))]
 
 
 def sym_singular_values(A):

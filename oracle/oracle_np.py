@@ -217,3 +217,80 @@ def closed_form(frame_pose, offsets, points):
     T[:3, :3] = U @ Vt
     T[:3, 3] = tlc
     return T, unobservable, AtA, A.T @ b
+
+
+# --- LineFittingCeres (LaseCamCalCeres.cpp:385-433) with a generic restatement of the same Ceres loop ----------------
+def trust_region_lm(evaluate_fn, plus_fn, x0, max_num_iterations, gradient_norm_fn):
+    """Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy + DENSE_QR, defaults as in solve() above, for any
+    residual model: evaluate_fn(x) -> (cost, corrected residuals, corrected Jacobian)."""
+    ftol, gtol, ptol = 1e-6, 1e-10, 1e-8
+    radius, dec = 1e4, 2.0
+    x = np.array(x0, dtype=float)
+    x_norm = np.linalg.norm(x)
+    cost, r, J = evaluate_fn(x)
+    g = J.T @ r
+    scale = 1.0 / (1.0 + np.sqrt(np.sum(J * J, axis=0)))
+    J = J * scale
+    n = J.shape[1]
+    trace = [dict(iteration=0, cost=cost, ok=True, gmax=gradient_norm_fn(x, g), radius=radius)]
+    reuse, invalid, diag, term = False, 0, None, None
+    while True:
+        last = trace[-1]
+        if last["iteration"] >= max_num_iterations:
+            term = "NO_CONVERGENCE"; break
+        if last["ok"] and last["gmax"] <= gtol:
+            term = "CONVERGENCE_GRADIENT"; break
+        if radius <= 1e-32:
+            term = "CONVERGENCE_MIN_RADIUS"; break
+        it = last["iteration"] + 1
+        if not reuse:
+            diag = np.clip(np.sum(J * J, axis=0), 1e-6, 1e32)
+        A = np.vstack([J, np.diag(np.sqrt(diag / radius))])
+        y = np.linalg.lstsq(A, np.concatenate([r, np.zeros(n)]), rcond=None)[0]
+        step = -y
+        reuse = True
+        mr = J @ step
+        model_change = -float(mr @ (r + mr / 2.0))
+        if not (np.all(np.isfinite(step)) and model_change > 0.0):
+            invalid += 1
+            if invalid >= 5:
+                term = "FAILURE"; break
+            radius /= dec; dec *= 2.0
+            trace.append(dict(iteration=it, cost=cost, ok=False, gmax=last["gmax"], radius=radius))
+            continue
+        invalid = 0
+        cand = plus_fn(x, step * scale)
+        cand_cost = evaluate_fn(cand)[0]
+        if np.linalg.norm(x - cand) <= ptol * (x_norm + ptol):
+            term = "CONVERGENCE_PARAMETER"; break
+        change = cost - cand_cost
+        if abs(change) <= ftol * cost:
+            term = "CONVERGENCE_FUNCTION"; break
+        rho = change / model_change
+        if rho > 1e-3:
+            x = cand
+            x_norm = np.linalg.norm(x)
+            cost, r, J = evaluate_fn(x)
+            g = J.T @ r
+            J = J * scale
+            radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3))
+            dec, reuse = 2.0, False
+            trace.append(dict(iteration=it, cost=cost, ok=True, gmax=gradient_norm_fn(x, g), radius=radius))
+        else:
+            radius /= dec; dec *= 2.0
+            trace.append(dict(iteration=it, cost=cand_cost, ok=False, gmax=0.0, radius=radius))
+    return x, term, trace
+
+
+def line_fit(points, line0=(0.0, 0.0), max_num_iterations=10, a=0.05):
+    """residual m0 x + m1 y + 1 (:391), CauchyLoss(0.05) (:416), max_num_iterations = 10 (:425)."""
+    xy = np.asarray(points, dtype=float)[:, :2]
+
+    def ev(m):
+        res = xy @ m + 1.0
+        summ = 1.0 + res * res / (a * a)
+        sq = np.sqrt(np.maximum(np.finfo(float).tiny, 1.0 / summ))
+        return 0.5 * float(np.sum(a * a * np.log(summ))), res * sq, xy * sq[:, None]
+
+    return trust_region_lm(ev, lambda x, d: x + d, np.array(line0, dtype=float), max_num_iterations,
+                           lambda x, g: float(np.max(np.abs(g))))

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "../camlasercalibratool_b200/csrc/clc_expand.cuh"
+#include "../camlasercalibratool_b200/csrc/clc_linefit.cuh"
 #include "../camlasercalibratool_b200/csrc/clc_lm.cuh"
 
 extern "C" {
@@ -59,6 +60,17 @@ void harness_gen_points(uint64_t seed, double sigma, int64_t frame, int64_t beam
     const double depth = -dl / (cx * nl[0] + sy * nl[1]) + clc::gen_noise(seed, sigma, frame, j);
     pts[3 * j] = depth * cx; pts[3 * j + 1] = depth * sy; pts[3 * j + 2] = 0.0;
   }
+}
+
+// the 2-parameter state machine of the batched line fit, driven exactly as the kernel does
+int harness_lm2_size() { return (int)sizeof(clc::Lm2); }
+void harness_lm2_init(void* st, double m0, double m1) { clc::lm2_init(*static_cast<clc::Lm2*>(st), m0, m1); }
+void harness_lm2_update(void* st, const double* sums6, int max_iter) { clc::lm2_update(*static_cast<clc::Lm2*>(st), sums6, max_iter); }
+int harness_lm2_done(const void* st) { return static_cast<const clc::Lm2*>(st)->done; }
+void harness_lm2_get(const void* st, double* cand2, double* x2, int* iteration, int* sweeps) {
+  const clc::Lm2* s = static_cast<const clc::Lm2*>(st);
+  cand2[0] = s->cand[0]; cand2[1] = s->cand[1]; x2[0] = s->x[0]; x2[1] = s->x[1];
+  *iteration = s->iteration; *sweeps = s->sweeps;
 }
 
 }  // extern "C"

@@ -259,3 +259,39 @@ def test_full_size_config2_properties(oracle):
         xs, s, tr = g.solve(X0)
         ang, dt = oracle.pose_error(xs, oracle.ground_truth()[1])
         assert ang < 1e-9 and dt < 1e-9 and s.termination in (1, 2, 3)
+
+
+def test_full_size_config3_and_config5_properties(oracle):
+    """BASELINE configs[2] and [4] at full size (10^5 frames x 2*10^3 points = 2*10^8 residuals, 4.8 GB; config 5 adds
+    2*10^5 board-edge residuals).  The oracle cannot sweep 2*10^8 residuals in test time, so: ground-truth recovery on
+    noise-free data, bit-reproducibility of a noisy solve, shard additivity of the sums, and an oracle comparison on a
+    random sample of frames read back from the device."""
+    from camlasercalibratool_b200 import Problem
+
+    N, M = 100_000, 2_000
+    gt = oracle.ground_truth()[1]
+    for edges in (False, True):
+        with Problem.synthetic(N, M, seed=11, sigma=0.0, with_edges=edges) as g:
+            assert g.algorithmic_bytes() == 24 * N * M + 40 * N + (56 * 2 * N if edges else 0) + 224
+            x, s, tr = g.solve(X0)
+            ang, dt = oracle.pose_error(x, gt)
+            # Ceres' parameter tolerance (1e-8 relative step) ends the solve once the step is ~1e-8: that is the accuracy
+            assert ang < 1e-7 and dt < 1e-7 and s.termination in (1, 2, 3), (edges, ang, dt, s.termination)
+        with Problem.synthetic(N, M, seed=11, sigma=0.01, with_edges=edges) as g:
+            xa, sa, tra = g.solve(X0)
+            xb, sb, trb = g.solve(X0)
+            assert np.array_equal(xa, xb) and [t.cost for t in tra] == [t.cost for t in trb]
+            ang, dt = oracle.pose_error(xa, gt)
+            assert ang < 1e-4 and dt < 1e-4  # 1 cm noise averaged over 2*10^8 points
+            xe = oracle.pose_plus(gt, np.array([0.01, -0.02, 0.015, 0.004, -0.003, 0.002]))
+            whole = pack_sums(*g.eval(xe))
+        halves = np.zeros(28)
+        for b, e in ((0, 37_000), (37_000, N)):
+            with Problem.synthetic(N, M, seed=11, sigma=0.01, with_edges=edges, frame_begin=b, frame_end=e) as gs:
+                halves += pack_sums(*gs.eval(xe))
+        np.testing.assert_allclose(halves, whole, rtol=0, atol=1e-11 * np.abs(whole).max())
+        # a 2000-frame sub-problem of the same stream, checked against the oracle
+        with Problem.synthetic(N, M, seed=11, sigma=0.01, with_edges=edges, frame_begin=50_000, frame_end=52_000) as gs:
+            d = gs.download()
+            p = oracle.Problem(d["frame_pose"], d["offsets"], d["points"], d["edge_points"])
+            assert_sums_close(gs.eval(xe), oracle.evaluate_normal(p, xe, num_threads=8))
