@@ -295,3 +295,44 @@ def test_full_size_config3_and_config5_properties(oracle):
             d = gs.download()
             p = oracle.Problem(d["frame_pose"], d["offsets"], d["points"], d["edge_points"])
             assert_sums_close(gs.eval(xe), oracle.evaluate_normal(p, xe, num_threads=8))
+
+
+def test_randomised_solves_follow_the_oracle(oracle):
+    """60 random problems (sizes, noise, gross outliers, starts from identity to far off, edges, loss on/off): the
+    on-device LM must take the oracle's decisions -- same termination reason, same number of iterations -- and end
+    within the north-star tolerance of it.  Guards against knife-edge divergences of the two arithmetic paths
+    (Cholesky on moment-expanded normal equations vs Householder QR on the materialised Jacobian)."""
+    rng = np.random.default_rng(2026)
+    gt = oracle.ground_truth()[1]
+    worst = (0.0, 0.0)
+    for trial in range(60):
+        n_frames = int(rng.integers(6, 90))
+        beams = int(rng.integers(8, 300))
+        sigma = float(rng.choice([0.0, 0.002, 0.01, 0.03]))
+        edges = bool(rng.integers(0, 4) == 0)
+        use_loss = bool(rng.integers(0, 5) != 0)
+        p = oracle.generate(n_frames, beams, seed=1000 + trial, sigma=sigma, exact_m=edges or bool(rng.integers(0, 2)),
+                            with_edges=edges, use_loss=use_loss)
+        pts = p.points.copy()
+        if rng.integers(0, 3) == 0 and len(pts) > 50:  # gross outliers, the reason the reference uses a robust loss
+            idx = rng.choice(len(pts), size=len(pts) // 25, replace=False)
+            pts[idx, :2] += rng.normal(size=(len(idx), 2)) * 0.5
+        p = oracle.Problem(p.frame_pose, p.offsets, pts, p.edge_points, use_loss=use_loss)
+        kind = trial % 3
+        if kind == 0:
+            x0 = X0
+        elif kind == 1:
+            x0 = oracle.pose_plus(gt, rng.normal(size=6) * 0.2)
+        else:
+            q = rng.normal(size=4)
+            x0 = np.concatenate([rng.normal(size=3) * 2, q / np.linalg.norm(q)])
+        with gpu_problem(p) as g:
+            x, s, tr = g.solve(x0)
+        xo, so, tro = oracle.solve(p, x0)
+        ang, dt = oracle.pose_error(x, xo)
+        worst = (max(worst[0], ang), max(worst[1], dt))
+        ctx = f"trial {trial}: frames {n_frames} beams {beams} sigma {sigma} edges {edges} loss {use_loss} start {kind}"
+        assert ang < TOL_ANG and dt < TOL_T, (ctx, ang, dt)
+        assert s.termination == so.termination and s.num_iterations == so.num_iterations, (ctx, s.termination, so.termination,
+                                                                                            s.num_iterations, so.num_iterations)
+    assert worst[0] < 1e-8 and worst[1] < 1e-8, worst
