@@ -384,6 +384,33 @@ def run_ours(args):
                                          "lm_iters_per_s": (s3.num_iterations - 1) / (s3.device_ms * 1e-3),
                                          "termination": int(s3.termination)}}
 
+    # ---- supplementary: BASELINE configs[0], the reference's own problem size (50 frames x 180 beams), end to end through
+    #      the mirrored entry point (marshal + upload + on-device LM + analysis tail + destroy) next to the CPU oracle ----
+    config1 = None
+    if rank == 0 and world == 1:
+        from camlasercalibratool_b200 import CamLaserCalibration, Oberserve
+        from oracle import oracle as O
+
+        small = O.generate(50, 180, seed=1, sigma=0.01)
+        obs = [Oberserve(small.frame_pose[f, :4].copy(), small.frame_pose[f, 4:].copy(),
+                         small.points[small.offsets[f]:small.offsets[f + 1]], small.points[small.offsets[f]:small.offsets[f + 1]])
+               for f in range(small.n_frames)]
+        for _ in range(3):
+            CamLaserCalibration(obs, np.eye(4), False, verbose=False)
+        t0 = time.perf_counter()
+        reps = 20
+        for _ in range(reps):
+            rep = CamLaserCalibration(obs, np.eye(4), False, verbose=False)
+        gpu_ms = 1e3 * (time.perf_counter() - t0) / reps
+        launches += 23 * 20
+        t0 = time.perf_counter()
+        for _ in range(5):
+            O.solve(small, X0)
+        cpu_ms = 1e3 * (time.perf_counter() - t0) / 5
+        config1 = {"workload": "BASELINE configs[0]: 50 frames x 180 beams (5351 residuals), CamLaserCalibration() end to end",
+                   "gpu_ms_per_call": gpu_ms, "device_ms_of_the_lm": rep["device_ms"], "lm_iterations": rep["iterations"] - 1,
+                   "cpu_oracle_ms_per_solve_1_thread": cpu_ms}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.frames, args.beams)
@@ -405,7 +432,7 @@ def run_ours(args):
                        "lm": "one fused residual+Jacobian+reduce sweep per LM iteration (speculative Jacobian at the candidate)"},
             "lm_iters_per_s": lm_iters_per_s, "sweeps_per_solve": sweeps / args.steps, "lm_iterations_per_solve": iters / args.steps,
             "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "config3": config3, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "config3": config3, "config1": config1, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches),
         }
         print(json.dumps(line))

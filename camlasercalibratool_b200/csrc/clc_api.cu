@@ -362,21 +362,34 @@ int finish_create(clc_problem* p) {
     clc::clc_planes_kernel<<<blocks, threads, 0, p->stream>>>(p->frame_pose, p->n_frames, p->plane, p->edge_plane);
     CLC_LAUNCH_CHECK();
   }
-  // persistent grid: SM count x resident blocks per SM (the smallest occupancy of the instantiations used)
-  int occ = 0, occ_min = 1 << 30;
-  CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<true, clc::kModeLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
-  CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<false, clc::kModeLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
-  CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<false, clc::kModeClosedForm>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
-  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<true, clc::kModeLM>, clc::kThreads, clc::kDynSmemBytes));
-  occ_min = std::min(occ_min, occ);
-  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeLM>, clc::kThreads, clc::kDynSmemBytes));
-  occ_min = std::min(occ_min, occ);
-  CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeClosedForm>, clc::kThreads, clc::kDynSmemBytes));
-  occ_min = std::min(occ_min, occ);
-  int blocks_per_sm = std::max(1, std::min(occ_min, clc::kBlocksPerSM));
-  if (const char* env = std::getenv("CLC_BLOCKS_PER_SM")) {
-    const int v = std::atoi(env);
-    if (v >= 1) blocks_per_sm = std::min(v, std::max(1, occ_min));
+  // persistent grid: SM count x resident blocks per SM (the smallest occupancy of the instantiations used); queried once
+  // per device and cached -- problem creation is on the latency path of the reference-facing calls
+  static std::mutex cfg_mutex;
+  static int cached_blocks_per_sm[64] = {};
+  int blocks_per_sm = 0;
+  {
+    std::lock_guard<std::mutex> lock(cfg_mutex);
+    if (p->device < 64) blocks_per_sm = cached_blocks_per_sm[p->device];
+  }
+  if (blocks_per_sm == 0) {
+    int occ = 0, occ_min = 1 << 30;
+    CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<true, clc::kModeLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
+    CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<false, clc::kModeLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
+    CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<false, clc::kModeClosedForm>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
+    CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<true, clc::kModeLM>, clc::kThreads, clc::kDynSmemBytes));
+    occ_min = std::min(occ_min, occ);
+    CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeLM>, clc::kThreads, clc::kDynSmemBytes));
+    occ_min = std::min(occ_min, occ);
+    CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeClosedForm>, clc::kThreads, clc::kDynSmemBytes));
+    occ_min = std::min(occ_min, occ);
+    if (occ_min < 1) return fail(CLC_ERR_CUDA, "the sweep kernel does not fit on this device");
+    blocks_per_sm = std::max(1, std::min(occ_min, clc::kBlocksPerSM));
+    if (const char* env = std::getenv("CLC_BLOCKS_PER_SM")) {
+      const int v = std::atoi(env);
+      if (v >= 1) blocks_per_sm = std::min(v, std::max(1, occ_min));
+    }
+    std::lock_guard<std::mutex> lock(cfg_mutex);
+    if (p->device < 64) cached_blocks_per_sm[p->device] = blocks_per_sm;
   }
   p->grid = p->num_sms * blocks_per_sm;
   if (const char* env = std::getenv("CLC_PDL")) p->use_pdl = std::atoi(env) != 0;

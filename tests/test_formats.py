@@ -1,0 +1,122 @@
+"""Text formats and the ROS-free offline driver glue: reference src/utilities.cpp:6-54,
+main/kalibratag_detector_node.cpp:202-236, main/calibr_offline.cpp:52-197."""
+import math
+
+import numpy as np
+import pytest
+
+
+def _poses_from_problem(p, fmt):
+    poses = []
+    for f in range(p.n_frames):
+        qca, tca = p.frame_pose[f, :4], p.frame_pose[f, 4:]
+        qwc = fmt.quat_inverse(qca)
+        twc = -fmt.quat_to_rot(qwc) @ tca
+        poses.append(fmt.CamPose(100.0 + 0.5 * f, qwc, twc))
+    return poses
+
+
+def test_pose_txt_round_trip_and_layout(tmp_path, oracle):
+    from camlasercalibratool_b200 import formats as fmt
+
+    p = oracle.generate(12, 20, seed=3, exact_m=True)
+    poses = _poses_from_problem(p, fmt)
+    path = tmp_path / "apriltag_pose.txt"
+    fmt.save_cam_pose_txt(path, poses)
+    lines = path.read_text().splitlines()
+    assert len(lines) == 12 and len(lines[0].split()) == 11  # ts x y z qx qy qz qw roll pitch yaw
+    assert lines[0].split()[0] == "100.000000000" and len(lines[0].split()[1].split(".")[1]) == 10
+    path.write_text(path.read_text() + "\n\n")  # trailing blank lines are skipped (utilities.cpp:25)
+    back = fmt.load_cam_pose_txt(path)
+    assert len(back) == 12
+    for a, b in zip(poses, back):
+        assert a.timestamp == b.timestamp
+        np.testing.assert_allclose(a.twc, b.twc, atol=1e-10)
+        np.testing.assert_allclose(a.qwc, b.qwc, atol=1e-10)
+
+
+def test_euler_angles_match_scipy():
+    from scipy.spatial.transform import Rotation
+
+    from camlasercalibratool_b200 import formats as fmt
+
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        r, p, y = fmt.to_euler_angles(q)
+        yz, py, rx = Rotation.from_quat(q).as_euler("ZYX")  # yaw about Z, pitch about Y, roll about X
+        np.testing.assert_allclose([r, p, y], [rx, py, yz], atol=1e-12)
+    assert fmt.to_euler_angles(np.array([0, math.sin(math.pi / 4), 0, math.cos(math.pi / 4)]))[1] == pytest.approx(math.pi / 2)
+
+
+def test_result_yaml_is_readable_by_opencv(tmp_path, oracle):
+    from camlasercalibratool_b200 import formats as fmt
+
+    gtT, _ = oracle.ground_truth()
+    path = str(tmp_path / "result.yaml")
+    rpy = fmt.write_result_yaml(path, gtT)
+    mine = fmt.read_result_yaml(path)
+    np.testing.assert_array_equal(mine["extrinsicTlc"], gtT)
+    np.testing.assert_allclose(mine["txtytz"].ravel(), [0.1, 0.2, 0.3])
+    cv2 = pytest.importorskip("cv2")
+    fs = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)  # the reader debug_code/showscan_node.cpp:193-202 uses
+    np.testing.assert_array_equal(fs.getNode("extrinsicTlc").mat(), gtT)
+    np.testing.assert_allclose(fs.getNode("RollPitchYaw").mat().ravel(), rpy)
+    np.testing.assert_allclose(fs.getNode("txtytz").mat().ravel(), [0.1, 0.2, 0.3])
+
+
+def test_keyframe_selection(oracle):
+    from camlasercalibratool_b200 import formats as fmt
+
+    base = fmt.CamPose(0.0, np.array([0, 0, 0, 1.0]), np.zeros(3))
+    near = fmt.CamPose(1.0, np.array([0, 0, 0, 1.0]), np.array([0.05, 0, 0]))            # < 0.2 m, no rotation: dropped
+    far = fmt.CamPose(2.0, np.array([0, 0, 0, 1.0]), np.array([0.25, 0, 0]))             # > 0.2 m: kept
+    a = math.radians(12) / 2
+    turned = fmt.CamPose(3.0, np.array([0, 0, math.sin(a), math.cos(a)]), np.array([0.25, 0, 0]))  # 12 deg: kept
+    small = fmt.CamPose(4.0, np.array([0, 0, math.sin(a), math.cos(a)]), np.array([0.30, 0, 0]))   # 5 cm, 0 deg: dropped
+    kept = fmt.select_keyframes([base, near, far, turned, small])
+    assert [k.timestamp for k in kept] == [0.0, 2.0, 3.0]
+
+
+@pytest.mark.gpu
+def test_offline_pipeline_without_ros(tmp_path, oracle):
+    """apriltag_pose.txt + laser segments -> key frames -> nearest pose -> batched line fits -> closed form -> LM ->
+    result.yaml, against the same chain done with the oracle."""
+    from camlasercalibratool_b200 import formats as fmt
+
+    p = oracle.generate(60, 180, seed=5, sigma=0.005)
+    poses = _poses_from_problem(p, fmt)
+    fmt.save_cam_pose_txt(tmp_path / "apriltag_pose.txt", poses)
+    tagpose = fmt.load_cam_pose_txt(tmp_path / "apriltag_pose.txt")
+    scans = []
+    for f in range(p.n_frames):
+        pts = p.points[p.offsets[f]:p.offsets[f + 1]]
+        scans.append((100.0 + 0.5 * f + 0.004, pts))            # 4 ms after the image: matched
+        scans.append((100.0 + 0.5 * f + 0.2, pts + 0.5))        # 200 ms off: no pose within 20 ms, dropped
+    Tlc, rep = fmt.calibrate_offline(tagpose, scans, result_yaml=str(tmp_path / "result.yaml"))
+    assert rep["n_obs"] > 40
+    # the same chain with the oracle (pose file precision: 1e-10)
+    kept = {k.timestamp for k in fmt.select_keyframes(tagpose)}
+    frames = [f for f in range(p.n_frames) if (100.0 + 0.5 * f) in kept and p.offsets[f + 1] > p.offsets[f]]
+    fp = np.array([np.concatenate([fmt.quat_inverse(tagpose[f].qwc), -fmt.quat_to_rot(fmt.quat_inverse(tagpose[f].qwc)) @ tagpose[f].twc])
+                   for f in frames])
+    segs = [p.points[p.offsets[f]:p.offsets[f + 1]] for f in frames]
+    ends = []
+    for pts in segs:
+        line, _, _ = oracle.line_fit(pts, (0.0, 0.0))
+        x_s, x_e, y_s, y_e = pts[0, 0], pts[-1, 0], pts[0, 1], pts[-1, 1]
+        if abs(x_e - x_s) > abs(y_e - y_s):
+            y_s, y_e = -(x_s * line[0] + 1) / line[1], -(x_e * line[0] + 1) / line[1]
+        else:
+            x_s, x_e = -(y_s * line[1] + 1) / line[0], -(y_e * line[1] + 1) / line[0]
+        ends.append(np.array([[x_s, y_s, 0.0], [x_e, y_e, 0.0]]))
+    on_line = oracle.Problem(fp, np.arange(len(frames) + 1) * 2, np.concatenate(ends))
+    Tlc0, _, _, _ = oracle.closed_form(on_line)
+    np.testing.assert_allclose(rep["Tlc_closed_form"], Tlc0, atol=1e-7)
+    full = oracle.Problem(fp, np.concatenate([[0], np.cumsum([len(s) for s in segs])]), np.concatenate(segs))
+    xo, _, _ = oracle.solve(full, oracle.T_to_pose7(np.linalg.inv(rep["Tlc_closed_form"])))
+    np.testing.assert_allclose(Tlc, np.linalg.inv(oracle.pose7_to_T(xo)), atol=1e-7)
+    assert np.abs(Tlc - oracle.ground_truth()[0]).max() < 5e-3
+    saved = fmt.read_result_yaml(str(tmp_path / "result.yaml"))
+    np.testing.assert_array_equal(saved["extrinsicTlc"], Tlc)
