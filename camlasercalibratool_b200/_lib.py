@@ -116,10 +116,12 @@ SIGNATURES = {
     "clc_problem_download": (C.c_int, [_P, c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p]),
     "clc_eval": (C.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p]),
     "clc_solve_lm": (C.c_int, [_P, c_double_p, C.POINTER(LmOptions), C.POINTER(LmSummary), C.POINTER(LmIteration), C.c_int]),
-    "clc_information": (C.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "clc_information": (C.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "clc_closed_form": (C.c_int, [_P, c_double_p, C.POINTER(C.c_int), c_double_p, c_double_p]),
     "clc_problem_line_fit": (C.c_int, [_P, c_double_p, C.c_int, c_double_p]),
     "clc_line_fit_points": (C.c_int, [c_double_p, C.c_int64, c_double_p, C.c_int]),
+    "clc_scan_segments": (C.c_int, [C.POINTER(C.c_float), C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
     "clc_T_to_pose7": (None, [c_double_p, c_double_p]),
     "clc_pose7_to_T": (None, [c_double_p, c_double_p]),
     "clc_shard_range": (C.c_int, [C.c_int64, c_int64_p, C.c_int, C.c_int, c_int64_p, c_int64_p]),

@@ -174,7 +174,9 @@ class Problem:
     def information(self, pose7):
         pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
         H, b, sv, chi = np.empty((6, 6)), np.empty(6), np.empty(6), C.c_double()
-        _lib.check(self._L.clc_information(self._h, _dp(pose7), _dp(H), _dp(b), C.byref(chi), _dp(sv)), "clc_information")
+        self.last_V = np.empty((6, 6))  # right singular vectors of H, columns ordered like sv
+        _lib.check(self._L.clc_information(self._h, _dp(pose7), _dp(H), _dp(b), C.byref(chi), _dp(sv), _dp(self.last_V)),
+                   "clc_information")
         return H, b, chi.value, sv
 
     def closed_form(self):
@@ -332,18 +334,18 @@ def CamLaserCalibration(obs, Tcl: np.ndarray, use_linefitting_data=True, use_bou
         T = pose7_to_T(x)
         Tcl[:3, :] = T[:3, :]  # :311-314
         H, b, chi, sv = p.information(x)  # :318-362
+        V = p.last_V
     report = dict(termination=TERMINATION.get(s.termination, "?"), iterations=s.num_iterations,
                   initial_cost=s.initial_cost, final_cost=s.final_cost, trace=trace, H=H, b=b, chi2=chi / 2.0,
-                  singular_values=sv, pose7=x, device_ms=s.device_ms, num_sweeps=s.num_sweeps)
+                  singular_values=sv, V=V, pose7=x, device_ms=s.device_ms, num_sweeps=s.num_sweeps)
     if verbose:
         print(f"LM (on device): {report['termination']}, {s.num_iterations} iterations, cost {s.initial_cost:.6e} -> "
               f"{s.final_cost:.6e}, {s.device_ms:.3f} ms")
         print("----- H singular values--------:\n", sv)
         n_null = int(np.sum(sv < 1e-8))  # :368-379
         if n_null > 0:
-            w, V = np.linalg.eigh(H)
             print("====== null space basis, it's means the unobservable direction for Tcl ======")
             print("       please note the unobservable direction is for Tcl, not for Tlc        ")
-            print(V[:, np.argsort(np.abs(w))[:n_null]])
+            print(V[:, 6 - n_null:])  # svd.matrixV().rightCols(n), :378
         print("\nrecover chi2: ", chi / 2.0)
     return report

@@ -718,7 +718,8 @@ int clc_eval(clc_problem* p, const double pose7[7], double H36[36], double g6[6]
   return CLC_OK;
 }
 
-int clc_information(clc_problem* p, const double pose7[7], double H36[36], double b6[6], double* chi, double sv6[6]) {
+int clc_information(clc_problem* p, const double pose7[7], double H36[36], double b6[6], double* chi, double sv6[6],
+                    double V36[36]) {
   if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
   // reference :318-381: no loss, no edge residuals, scale kept
   int rc = eval_common(p, pose7, false, false, clc::kModeLM, clc::kNumSums);
@@ -728,7 +729,18 @@ int clc_information(clc_problem* p, const double pose7[7], double H36[36], doubl
   if (H36) std::memcpy(H36, H, sizeof(H));
   if (b6) for (int i = 0; i < 6; ++i) b6[i] = -p->h_sums[21 + i];
   if (chi) *chi = 2.0 * p->h_sums[27];
-  if (sv6) sym_singular_values<6>(H, sv6);
+  if (sv6 || V36) {
+    // H is symmetric: singular values = |eigenvalues|, right singular vectors = eigenvectors (Eigen::JacobiSVD, :366)
+    double w[6], V[36];
+    sym_eig<6>(H, w, V);
+    int order[6] = {0, 1, 2, 3, 4, 5};
+    std::sort(order, order + 6, [&](int a, int b) { return std::fabs(w[a]) > std::fabs(w[b]); });
+    for (int c = 0; c < 6; ++c) {
+      if (sv6) sv6[c] = std::fabs(w[order[c]]);
+      if (V36)
+        for (int r = 0; r < 6; ++r) V36[r * 6 + c] = V[r * 6 + order[c]];
+    }
+  }
   return CLC_OK;
 }
 
@@ -898,6 +910,42 @@ int clc_line_fit_points(const double* points_xyz, int64_t n, double line[2], int
   rc = clc_problem_line_fit(p, line, max_num_iterations, nullptr);
   clc_problem_destroy(p);
   return rc;
+}
+
+int clc_scan_segments(const float* ranges, int64_t n_scans, int64_t n_beams, double angle_min, double angle_increment,
+                      double range_min, int32_t* seg_start, int32_t* seg_end, int device) {
+  if (!ranges || n_scans < 0 || n_beams < 0 || !seg_start || !seg_end) return fail(CLC_ERR_INVALID, "bad scan arguments");
+  if (n_scans == 0) return CLC_OK;
+  int count = 0;
+  CLC_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0) CLC_CUDA(cudaGetDevice(&device));
+  if (device >= count) return fail(CLC_ERR_INVALID, "device ordinal out of range");
+  CLC_CUDA(cudaSetDevice(device));
+  float* d_r = nullptr;
+  int *d_s = nullptr, *d_e = nullptr;
+  cudaStream_t st;
+  CLC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaError_t e = cudaMallocAsync(&d_r, sizeof(float) * (size_t)n_scans * (size_t)std::max<int64_t>(n_beams, 1), st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_s, sizeof(int) * n_scans, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_e, sizeof(int) * n_scans, st);
+  if (e == cudaSuccess && n_beams > 0)
+    e = cudaMemcpyAsync(d_r, ranges, sizeof(float) * (size_t)n_scans * (size_t)n_beams, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    clc::clc_scan_segments_kernel<<<(unsigned)((n_scans + 127) / 128), 128, 0, st>>>(d_r, n_scans, n_beams, angle_min,
+                                                                                   angle_increment, range_min, d_s, d_e);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(seg_start, d_s, sizeof(int) * n_scans, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(seg_end, d_e, sizeof(int) * n_scans, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (d_r) cudaFreeAsync(d_r, st);
+  if (d_s) cudaFreeAsync(d_s, st);
+  if (d_e) cudaFreeAsync(d_e, st);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (e != cudaSuccess) return fail(CLC_ERR_CUDA, cudaGetErrorString(e));
+  return CLC_OK;
 }
 
 // ---- multi-GPU --------------------------------------------------------------------------------------------------

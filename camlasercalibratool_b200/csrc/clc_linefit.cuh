@@ -131,7 +131,98 @@ CLC_HD void lm2_update(Lm2& s, const double* sums, int max_num_iterations) {
   }
 }
 
+// ---- scan preparation: TranScanToPoints (reference src/utilities.cpp:181-215) + AutoGetLinePts (reference
+//      src/selectScanPoints.cpp:17-190, without its OpenCV drawing) -------------------------------------------------------
+// One beam of a LaserScan as the reference turns it into a point: (1000, 1000) marks an invalid range.
+CLC_HD void scan_point(const float* ranges, int64_t i, double angle_min, double angle_increment, double range_min, double* x,
+                       double* y) {
+  const float range = ranges[i];
+  if (range < 30.0 && range >= range_min) {
+    const double ang = angle_min + (double)i * angle_increment;
+    *x = (double)range * cos(ang);
+    *y = (double)range * sin(ang);
+  } else {
+    *x = 1000.0;
+    *y = 1000.0;
+  }
+}
+
+// The longest continuous segment in the +-80 degree front sector; inclusive index range, or start = end = -1.
+CLC_HD void auto_get_line_pts(const float* ranges, int64_t n, double angle_min, double angle_increment, double range_min,
+                              int* seg_start_out, int* seg_end_out) {
+  *seg_start_out = -1;
+  *seg_end_out = -1;
+  if (n <= 0) return;
+  auto pt = [&](int64_t i, double* x, double* y) { scan_point(ranges, i, angle_min, angle_increment, range_min, x, y); };
+  auto nrm = [&](int64_t i) {
+    double x, y;
+    pt(i, &x, &y);
+    return sqrt(x * x + y * y);
+  };
+  const int64_t id = n / 2, delta = (int64_t)(80 / 0.3);
+  const int64_t id_left = id + delta < n - 1 ? id + delta : n - 1;
+  const int64_t id_right = id - delta > 0 ? id - delta : 0;
+  const double dist_thre = 0.05, range_max = 100;
+  const int skip = 3;
+  int64_t best_cnt = -1;
+  int64_t cur = id_right, next = cur + skip, seg_start = 0, seg_end = 0;
+  bool new_seg = true;
+  double d_cur = nrm(cur);
+  for (int64_t i = id_right; i < id_left - skip; i += skip) {
+    if (new_seg) { seg_start = cur; seg_end = next; new_seg = false; }
+    const double d1 = d_cur, d2 = nrm(next);
+    if (d1 < range_max && d2 < range_max) {
+      if (fabs(d1 - d2) < dist_thre) {
+        seg_end = next;
+      } else {
+        new_seg = true;
+        double xs, ys, xe, ye;
+        pt(seg_start, &xs, &ys);
+        pt(seg_end, &xe, &ye);
+        const double ds = sqrt(xs * xs + ys * ys), de = sqrt(xe * xe + ye * ye);
+        if (sqrt((xs - xe) * (xs - xe) + (ys - ye) * (ys - ye)) > 0.2 && ds < 2 && de < 2 && seg_end - seg_start > 50) {
+          int64_t s = seg_start, e = seg_end;
+          for (int j = 1; j < 4; ++j) {
+            const int64_t bp = seg_end + j;
+            if (bp < n && fabs(de - nrm(bp)) < dist_thre) e = bp;
+          }
+          for (int j = -1; j > -4; --j) {
+            const int64_t bp = seg_start + j;
+            if (bp >= 0 && fabs(ds - nrm(bp)) < dist_thre) s = bp;
+          }
+          if (e - s > best_cnt) {
+            best_cnt = e - s;
+            *seg_start_out = (int)s;
+            *seg_end_out = (int)e;
+          }
+        }
+      }
+      cur = next;
+      d_cur = d2;
+      next += skip;
+    } else {
+      if (d1 > range_max) {
+        cur = next;
+        d_cur = d2;
+      }
+      next += skip;
+    }
+  }
+}
+
 #if defined(__CUDACC__)
+// one thread per scan: the walk is inherently sequential (about 180 steps), the batch is the parallelism
+__global__ void clc_scan_segments_kernel(const float* __restrict__ ranges, int64_t n_scans, int64_t n_beams, double angle_min,
+                                         double angle_increment, double range_min, int* __restrict__ seg_start,
+                                         int* __restrict__ seg_end) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scans) return;
+  int a, b;
+  auto_get_line_pts(ranges + s * n_beams, n_beams, angle_min, angle_increment, range_min, &a, &b);
+  seg_start[s] = a;
+  seg_end[s] = b;
+}
+
 // lines[f*2..+2]: start value in, fitted line out; info[f*4..+4] (optional): termination, iterations, sweeps, final cost
 __global__ void __launch_bounds__(256) clc_line_fit_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                                           const int64_t* __restrict__ offsets, int64_t n_frames,

@@ -115,6 +115,41 @@ def read_result_yaml(path):
     return out
 
 
+# ---- scans: LaserScan ranges -> points -> board segment ---------------------------------------------------------------
+def scan_to_points(ranges, angle_min, angle_increment, range_min):
+    """reference src/utilities.cpp:181-215 TranScanToPoints (host data preparation; invalid beams -> (1000,1000,0))."""
+    r = np.asarray(ranges, dtype=np.float32)
+    ang = angle_min + np.arange(r.shape[-1], dtype=float) * angle_increment
+    ok = (r < 30.0) & (r >= range_min)
+    with np.errstate(invalid="ignore"):
+        x = np.where(ok, r.astype(float) * np.cos(ang), 1000.0)
+        y = np.where(ok, r.astype(float) * np.sin(ang), 1000.0)
+    return np.stack([x, y, np.zeros_like(x)], axis=-1)
+
+
+def auto_get_line_segments(ranges, angle_min, angle_increment, range_min, device=-1):
+    """Batched AutoGetLinePts (reference src/selectScanPoints.cpp:17-190) on the GPU: ranges[n_scans, n_beams] float32 ->
+    (seg_start[n_scans], seg_end[n_scans]) inclusive beam indices, -1 where no board segment was found."""
+    import ctypes as C
+
+    from . import _lib
+
+    r = np.ascontiguousarray(ranges, dtype=np.float32).reshape(len(ranges), -1)
+    s = np.empty(r.shape[0], dtype=np.int32)
+    e = np.empty(r.shape[0], dtype=np.int32)
+    _lib.check(_lib.load().clc_scan_segments(r.ctypes.data_as(C.POINTER(C.c_float)), r.shape[0], r.shape[1], float(angle_min),
+                                             float(angle_increment), float(range_min), s.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             e.ctypes.data_as(C.POINTER(C.c_int32)), int(device)), "clc_scan_segments")
+    return s, e
+
+
+def segments_from_scans(timestamps, ranges, angle_min, angle_increment, range_min):
+    """reference main/calibr_offline.cpp:88-100: [(timestamp, points[n,3])] of the scans in which a board segment was found."""
+    pts = scan_to_points(ranges, angle_min, angle_increment, range_min)
+    s, e = auto_get_line_segments(ranges, angle_min, angle_increment, range_min)
+    return [(float(t), pts[k, s[k]:e[k] + 1]) for k, t in enumerate(timestamps) if s[k] >= 0]
+
+
 # ---- the offline driver, without ROS -----------------------------------------------------------------------------------
 def select_keyframes(tagpose, dist_min=0.20, theta_min=3.1415926 * 10 / 180.0):
     """reference main/calibr_offline.cpp:62-78."""

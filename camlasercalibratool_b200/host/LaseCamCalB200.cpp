@@ -160,8 +160,8 @@ void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl,
     for (int c = 0; c < 4; ++c) Tcl(r, c) = T[r * 4 + c];  // :311-314 (bottom row untouched)
 
   // ---- analysis tail (:316-381) ----
-  double H[36], b[6], chi = 0.0, sv[6];
-  if (clc_information(p, pose, H, b, &chi, sv) == CLC_OK) {
+  double H[36], b[6], chi = 0.0, sv[6], V[36];
+  if (clc_information(p, pose, H, b, &chi, sv, V) == CLC_OK) {
     std::cout << "----- H singular values--------:\n";
     for (int i = 0; i < 6; ++i) std::cout << sv[i] << "\n";
     int n_null = 0;
@@ -170,9 +170,8 @@ void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl,
     if (n_null > 0) {
       std::cout << "====== null space basis, it's means the unobservable direction for Tcl ======" << std::endl;
       std::cout << "       please note the unobservable direction is for Tcl, not for Tlc        " << std::endl;
-      std::cout << "       (" << n_null << " singular value(s) below 1e-8; H follows)\n";
-      for (int r = 0; r < 6; ++r) {
-        for (int c = 0; c < 6; ++c) std::cout << H[r * 6 + c] << " ";
+      for (int r = 0; r < 6; ++r) {  // svd.matrixV().rightCols(n), :378
+        for (int c = 6 - n_null; c < 6; ++c) std::cout << V[r * 6 + c] << " ";
         std::cout << "\n";
       }
     }

@@ -148,9 +148,11 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt, clc
                  clc_lm_iteration* trace, int trace_cap);
 
 /* replaces: the analysis tail, reference src/LaseCamCalCeres.cpp:318-381: un-robustified H, b = -J^T r,
- * chi = sum r^2 (scale kept, no edge residuals), singular values of H (descending). */
+ * chi = sum r^2 (scale kept, no edge residuals), singular values of H (descending) and the matching right singular
+ * vectors as the columns of V36 (row-major 6x6): the last n columns span the null space the reference prints when n
+ * singular values are below 1e-8 (:368-379).  Any output may be NULL. */
 int clc_information(clc_problem* p, const double pose7[7], double H36[36], double b6[6], double* chi,
-                    double singular_values6[6]);
+                    double singular_values6[6], double V36[36]);
 
 /* replaces: CamLaserCalClosedSolution(), reference src/LaseCamCalCeres.cpp:112-203.  Tlc16 row-major.
  * AtA81/Atb9 (the 9x9 normal equations) may be NULL. */
@@ -165,6 +167,13 @@ int clc_closed_form(clc_problem* p, double Tlc16[16], int* unobservable, double 
 int clc_problem_line_fit(clc_problem* p, double* lines, int max_num_iterations, double* info);
 /* The reference's per-scan call shape: one scan of n points (AoS xyz, z ignored), line[2] in/out. */
 int clc_line_fit_points(const double* points_xyz, int64_t n, double line[2], int max_num_iterations);
+
+/* replaces: TranScanToPoints() + AutoGetLinePts(), reference src/utilities.cpp:181-215 and src/selectScanPoints.cpp:17-190
+ * (without the OpenCV debug drawing), batched over scans: for every LaserScan (n_beams float ranges, angle of beam i =
+ * angle_min + i * angle_increment) the inclusive beam-index range [seg_start, seg_end] of the laser segment on the board,
+ * or -1/-1 when none is found.  Host arrays in/out; device = CUDA ordinal or -1. */
+int clc_scan_segments(const float* ranges, int64_t n_scans, int64_t n_beams, double angle_min, double angle_increment,
+                      double range_min, int32_t* seg_start, int32_t* seg_end, int device);
 
 /* Eigen-equivalent conversions used on both sides of the boundary (reference :215-219 and :311-314). */
 void clc_T_to_pose7(const double T16[16], double pose7[7]);

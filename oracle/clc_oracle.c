@@ -816,6 +816,77 @@ int oracle_solve(const oracle_problem* p, double pose7[7], const oracle_options*
 }
 
 /* ------------------------------------------------------------------------------------------------------ */
+/* Scan preparation: src/utilities.cpp:181-215 and src/selectScanPoints.cpp:17-190                        */
+/* ------------------------------------------------------------------------------------------------------ */
+void oracle_scan_to_points(const float* ranges, int64_t n, double angle_min, double angle_increment, double range_min,
+                           double* points) {
+  for (int64_t i = 0; i < n; ++i) {
+    const double ang = angle_min + (double)i * angle_increment;
+    const float range = ranges[i];
+    if (range < 30.0 && range >= range_min) { /* range_cutoff = 30 (:205) */
+      points[3 * i] = (double)range * cos(ang);
+      points[3 * i + 1] = (double)range * sin(ang);
+    } else {
+      points[3 * i] = 1000.0;
+      points[3 * i + 1] = 1000.0;
+    }
+    points[3 * i + 2] = 0.0;
+  }
+}
+
+static inline double norm_xy(const double* points, int64_t i) {
+  return sqrt(points[3 * i] * points[3 * i] + points[3 * i + 1] * points[3 * i + 1]);
+}
+
+int oracle_auto_get_line_pts(const double* points, int64_t n, int64_t* start, int64_t* end) {
+  if (n <= 0) return 0;
+  const int64_t id = n / 2;
+  const int64_t delta = (int64_t)(80 / 0.3); /* :41 */
+  const int64_t id_left = id + delta < n - 1 ? id + delta : n - 1;
+  const int64_t id_right = id - delta > 0 ? id - delta : 0;
+  const double dist_thre = 0.05, range_max = 100;
+  const int skip = 3;
+  int64_t best_start = -1, best_end = -1, best_cnt = -1;
+  int64_t cur = id_right, next = cur + skip, seg_start = 0, seg_end = 0;
+  int new_seg = 1;
+  for (int64_t i = id_right; i < id_left - skip; i += skip) { /* :58 */
+    if (new_seg) { seg_start = cur; seg_end = next; new_seg = 0; }
+    const double d1 = norm_xy(points, cur), d2 = norm_xy(points, next);
+    if (d1 < range_max && d2 < range_max) {
+      if (fabs(d1 - d2) < dist_thre) {
+        seg_end = next;
+      } else {
+        new_seg = 1;
+        const double dx = points[3 * seg_start] - points[3 * seg_end], dy = points[3 * seg_start + 1] - points[3 * seg_end + 1];
+        if (sqrt(dx * dx + dy * dy) > 0.2 && norm_xy(points, seg_start) < 2 && norm_xy(points, seg_end) < 2 &&
+            seg_end - seg_start > 50) { /* :79-82 */
+          /* boundary extension (:103-129); the reference indexes with .at() and would throw outside [0,n): skipped here */
+          int64_t s = seg_start, e = seg_end;
+          for (int j = 1; j < 4; ++j) {
+            const int64_t bp = seg_end + j;
+            if (bp < n && fabs(norm_xy(points, seg_end) - norm_xy(points, bp)) < dist_thre) e = bp;
+          }
+          for (int j = -1; j > -4; --j) {
+            const int64_t bp = seg_start + j;
+            if (bp >= 0 && fabs(norm_xy(points, seg_start) - norm_xy(points, bp)) < dist_thre) s = bp;
+          }
+          if (e - s > best_cnt) { best_cnt = e - s; best_start = s; best_end = e; } /* :136-146, first maximum wins */
+        }
+      }
+      cur = next;
+      next += skip;
+    } else {
+      if (d1 > range_max) cur = next;
+      next += skip;
+    }
+  }
+  if (best_cnt < 0) return 0;
+  *start = best_start;
+  *end = best_end;
+  return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------------ */
 /* LineFittingCeres, LaseCamCalCeres.cpp:385-433                                                          */
 /* ------------------------------------------------------------------------------------------------------ */
 

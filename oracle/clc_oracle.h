@@ -147,6 +147,13 @@ int oracle_closed_form(const oracle_problem* p, double Tlc16[16], int* unobserva
 int oracle_line_fit(const double* points, int64_t n, double line[2], int max_num_iterations, oracle_summary* summary,
                     oracle_iteration* trace, int trace_cap);
 
+/* TranScanToPoints (src/utilities.cpp:181-215): float ranges -> xyz points, invalid beams -> (1000,1000,0). */
+void oracle_scan_to_points(const float* ranges, int64_t n, double angle_min, double angle_increment, double range_min,
+                           double* points);
+/* AutoGetLinePts (src/selectScanPoints.cpp:17-190) without the OpenCV drawing: the longest continuous segment in the
+ * +-80 degree front sector.  Returns 1 and the inclusive index range [start, end] of the chosen segment, else 0. */
+int oracle_auto_get_line_pts(const double* points, int64_t n, int64_t* start, int64_t* end);
+
 /* Small dense helpers exposed for the tests: singular values (descending) of a symmetric n x n matrix (n <= 9). */
 void oracle_sym_singular_values(const double* A, int n, double* sv);
 

@@ -132,6 +132,8 @@ def lib():
         L.oracle_information.argtypes = [C.POINTER(_Problem), dp, dp, dp, dp, dp]
         L.oracle_closed_form.argtypes = [C.POINTER(_Problem), dp, C.POINTER(C.c_int), dp, dp]
         L.oracle_sym_singular_values.argtypes = [dp, C.c_int, dp]
+        L.oracle_scan_to_points.argtypes = [C.POINTER(C.c_float), C.c_int64, C.c_double, C.c_double, C.c_double, dp]
+        L.oracle_auto_get_line_pts.argtypes = [dp, C.c_int64, ip, ip]
         L.oracle_line_fit.argtypes = [dp, C.c_int64, dp, C.c_int, C.POINTER(Summary), C.POINTER(Iteration), C.c_int]
         L.oracle_gen_ground_truth.argtypes = [dp, dp]
         L.oracle_gen_frames.argtypes = [C.POINTER(_GenDesc), dp, ip]
@@ -305,6 +307,22 @@ def closed_form(p: Problem):
     un = C.c_int()
     lib().oracle_closed_form(C.byref(p._c), _dp(T), C.byref(un), _dp(AtA), _dp(Atb))
     return T.reshape(4, 4), bool(un.value), AtA, Atb
+
+
+def scan_to_points(ranges, angle_min, angle_increment, range_min):
+    r = np.ascontiguousarray(ranges, dtype=np.float32)
+    pts = np.empty((r.shape[0], 3))
+    lib().oracle_scan_to_points(r.ctypes.data_as(C.POINTER(C.c_float)), r.shape[0], angle_min, angle_increment, range_min, _dp(pts))
+    return pts
+
+
+def auto_get_line_pts(points):
+    """(start, end) inclusive indices of the chosen segment, or None."""
+    pts = _f64(points, (-1, 3))
+    s, e = C.c_int64(), C.c_int64()
+    if not lib().oracle_auto_get_line_pts(_dp(pts), pts.shape[0], C.byref(s), C.byref(e)):
+        return None
+    return s.value, e.value
 
 
 def line_fit(points, line0=(0.0, 0.0), max_num_iterations=10, trace_cap=64):

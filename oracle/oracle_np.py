@@ -294,3 +294,57 @@ def line_fit(points, line0=(0.0, 0.0), max_num_iterations=10, a=0.05):
 
     return trust_region_lm(ev, lambda x, d: x + d, np.array(line0, dtype=float), max_num_iterations,
                            lambda x, g: float(np.max(np.abs(g))))
+
+
+# --- scan preparation (src/utilities.cpp:181-215, src/selectScanPoints.cpp:17-190), literal python loops -----------------
+def scan_to_points(ranges, angle_min, angle_increment, range_min):
+    r = np.asarray(ranges, dtype=np.float32)
+    ang = angle_min + np.arange(len(r), dtype=float) * angle_increment
+    ok = (r < 30.0) & (r >= range_min)
+    pts = np.zeros((len(r), 3))
+    pts[:, 0] = np.where(ok, r.astype(float) * np.cos(ang), 1000.0)
+    pts[:, 1] = np.where(ok, r.astype(float) * np.sin(ang), 1000.0)
+    return pts
+
+
+def auto_get_line_pts(points):
+    n = len(points)
+    if n == 0:
+        return None
+    nrm = lambda i: float(np.hypot(points[i][0], points[i][1]))  # noqa: E731
+    idc = n // 2
+    delta = int(80 / 0.3)
+    id_left, id_right = min(idc + delta, n - 1), max(idc - delta, 0)
+    segs = []
+    cur, nxt, new_seg, seg = id_right, id_right + 3, True, [0, 0]
+    for _ in range(id_right, id_left - 3, 3):
+        if new_seg:
+            seg, new_seg = [cur, nxt], False
+        d1, d2 = nrm(cur), nrm(nxt)
+        if d1 < 100 and d2 < 100:
+            if abs(d1 - d2) < 0.05:
+                seg[1] = nxt
+            else:
+                new_seg = True
+                dist = float(np.hypot(points[seg[0]][0] - points[seg[1]][0], points[seg[0]][1] - points[seg[1]][1]))
+                if dist > 0.2 and nrm(seg[0]) < 2 and nrm(seg[1]) < 2 and seg[1] - seg[0] > 50:
+                    segs.append(list(seg))
+            cur, nxt = nxt, nxt + 3
+        else:
+            if d1 > 100:
+                cur = nxt
+            nxt += 3
+    out = []
+    for s0, e0 in segs:
+        s, e = s0, e0
+        for j in (1, 2, 3):
+            if e0 + j < n and abs(nrm(e0) - nrm(e0 + j)) < 0.05:
+                e = e0 + j
+        for j in (-1, -2, -3):
+            if s0 + j >= 0 and abs(nrm(s0) - nrm(s0 + j)) < 0.05:
+                s = s0 + j
+        out.append((s, e))
+    if not out:
+        return None
+    best = max(range(len(out)), key=lambda k: (out[k][1] - out[k][0], -k))
+    return out[best]

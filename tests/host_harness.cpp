@@ -62,6 +62,9 @@ void harness_gen_points(uint64_t seed, double sigma, int64_t frame, int64_t beam
   }
 }
 
+void harness_auto_get_line_pts(const float* ranges, int64_t n, double a0, double inc, double rmin, int* s, int* e) {
+  clc::auto_get_line_pts(ranges, n, a0, inc, rmin, s, e);
+}
 // the 2-parameter state machine of the batched line fit, driven exactly as the kernel does
 int harness_lm2_size() { return (int)sizeof(clc::Lm2); }
 void harness_lm2_init(void* st, double m0, double m1) { clc::lm2_init(*static_cast<clc::Lm2*>(st), m0, m1); }

@@ -120,3 +120,61 @@ def test_offline_pipeline_without_ros(tmp_path, oracle):
     assert np.abs(Tlc - oracle.ground_truth()[0]).max() < 5e-3
     saved = fmt.read_result_yaml(str(tmp_path / "result.yaml"))
     np.testing.assert_array_equal(saved["extrinsicTlc"], Tlc)
+
+
+def synthetic_scans(n_scans, n_beams=1081, seed=0):
+    """LaserScan-like ranges: smooth walls at 3.5-6.5 m, 1 % dropped beams, and (3 of 4 scans) a flat board 0.6-1.5 m away
+    inside the front sector."""
+    rng = np.random.default_rng(seed)
+    a0, inc = -2.356, 4.712 / (n_beams - 1)
+    ang = a0 + np.arange(n_beams) * inc
+    out = np.empty((n_scans, n_beams), dtype=np.float32)
+    for k in range(n_scans):
+        r = (5 + np.sin(ang * 3 + rng.uniform(0, 6)) * 1.5 + rng.normal(size=n_beams) * 0.01).astype(np.float32)
+        if k % 4 != 0:
+            c, w, d = rng.uniform(-0.6, 0.6), rng.uniform(0.15, 0.35), rng.uniform(0.6, 1.5)
+            m = np.abs(ang - c) < w
+            r[m] = (d / np.cos(ang[m] - c) + rng.normal(size=int(m.sum())) * 0.003).astype(np.float32)
+        r[rng.random(n_beams) < 0.01] = np.inf
+        out[k] = r
+    return out, a0, inc
+
+
+def test_scan_preparation_restatements_agree(harness, oracle, oracle_np):
+    """TranScanToPoints + AutoGetLinePts: C oracle == numpy twin == the product's host/device code (host build)."""
+    import ctypes as C
+
+    from camlasercalibratool_b200 import formats as fmt
+
+    ranges, a0, inc = synthetic_scans(120, seed=3)
+    harness.L.harness_auto_get_line_pts.argtypes = [C.POINTER(C.c_float), C.c_int64, C.c_double, C.c_double, C.c_double,
+                                                    C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    found = 0
+    for r in ranges:
+        p = oracle.scan_to_points(r, a0, inc, 0.05)
+        np.testing.assert_allclose(p, oracle_np.scan_to_points(r, a0, inc, 0.05), atol=1e-12)
+        np.testing.assert_allclose(p, fmt.scan_to_points(r, a0, inc, 0.05), atol=1e-12)
+        ref = oracle.auto_get_line_pts(p)
+        assert ref == oracle_np.auto_get_line_pts(p)
+        s, e = C.c_int(), C.c_int()
+        harness.L.harness_auto_get_line_pts(r.ctypes.data_as(C.POINTER(C.c_float)), len(r), a0, inc, 0.05, C.byref(s), C.byref(e))
+        assert (ref is None and s.value == -1) or ref == (s.value, e.value)
+        found += ref is not None
+    assert 60 < found <= 90  # the scans with a board (3 of 4) are found, the board-less ones are not
+    # edge cases: empty scan, all-invalid scan, short scan
+    assert oracle.auto_get_line_pts(np.zeros((0, 3))) is None
+    assert oracle.auto_get_line_pts(oracle.scan_to_points(np.full(500, np.inf, dtype=np.float32), a0, inc, 0.05)) is None
+    assert oracle.auto_get_line_pts(oracle.scan_to_points(np.full(40, 1.0, dtype=np.float32), a0, inc, 0.05)) is None
+
+
+@pytest.mark.gpu
+def test_batched_scan_segments_match_oracle(oracle):
+    from camlasercalibratool_b200 import formats as fmt
+
+    ranges, a0, inc = synthetic_scans(2000, seed=4)
+    s, e = fmt.auto_get_line_segments(ranges, a0, inc, 0.05)
+    for k in range(0, 2000, 7):
+        ref = oracle.auto_get_line_pts(oracle.scan_to_points(ranges[k], a0, inc, 0.05))
+        assert (ref is None and s[k] == -1 and e[k] == -1) or ref == (int(s[k]), int(e[k])), k
+    segs = fmt.segments_from_scans(np.arange(2000) * 0.025, ranges, a0, inc, 0.05)
+    assert len(segs) == int(np.sum(s >= 0)) and all(len(p) == e[k] - s[k] + 1 for (t, p), k in zip(segs, np.nonzero(s >= 0)[0]))

@@ -336,3 +336,28 @@ def test_randomised_solves_follow_the_oracle(oracle):
         assert s.termination == so.termination and s.num_iterations == so.num_iterations, (ctx, s.termination, so.termination,
                                                                                             s.num_iterations, so.num_iterations)
     assert worst[0] < 1e-8 and worst[1] < 1e-8, worst
+
+
+def test_unobservable_configuration_reports_the_null_space(oracle):
+    """The reference's teaching case (calibr_simulation.cpp:50-51: boards rotated about one camera axis only): H loses
+    rank, and the analysis tail must hand back the null-space directions (svd.matrixV().rightCols(n), :368-379)."""
+    rng = np.random.default_rng(0)
+    fp, pts, off = [], [], [0]
+    for f in range(40):  # only pitch: Rca = Ry(angle); tca = (0, 0, z): one translation direction is unobservable
+        a = rng.uniform(-np.pi / 6, np.pi / 6)
+        q = np.array([0.0, np.sin(a / 2), 0.0, np.cos(a / 2)])
+        t = np.array([0.0, 0.0, rng.uniform(1, 5)])
+        fp.append(np.concatenate([q, t]))
+    base = oracle.generate(40, 60, seed=1, exact_m=True)
+    p = oracle.Problem(np.array(fp), base.offsets, base.points)
+    x = oracle.ground_truth()[1]
+    with gpu_problem(p) as g:
+        H, b, chi, sv = g.information(x)
+        V = g.last_V
+    rH, rb, rchi, rsv = oracle.information(p, x)
+    np.testing.assert_allclose(sv, rsv, rtol=1e-9, atol=1e-12)
+    n_null = int(np.sum(sv < 1e-8))
+    assert n_null >= 1
+    np.testing.assert_allclose(V.T @ V, np.eye(6), atol=1e-12)            # orthonormal
+    np.testing.assert_allclose(H @ V, V * sv[None, :], atol=1e-9 * sv[0])  # H v_k = sigma_k v_k
+    assert np.abs(H @ V[:, 6 - n_null:]).max() < 1e-7
