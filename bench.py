@@ -266,8 +266,21 @@ def run_ours(args):
             dist.all_gather_object(out, blob)
             return out
 
+        p2p_note = "fused into the sweep kernel (NVLink peer stores, sequence-tagged words, rank-order sum)"
         if not args.nccl_allreduce:
-            comm.enable_p2p(all_gather)  # fused in-kernel all-reduce over NVLink peer memory
+            try:
+                comm.enable_p2p(all_gather)  # fused in-kernel all-reduce over NVLink peer memory
+            except Exception as exc:  # no peer access between these GPUs: the NCCL path still works
+                args.nccl_allreduce = True
+                p2p_note = f"peer exchange unavailable ({exc}); "
+            ok = torch.tensor([0 if args.nccl_allreduce else 1], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks must use the same mode
+            if int(ok.item()) == 0 and not args.nccl_allreduce:
+                args.nccl_allreduce = True
+                comm.close()
+                uid = [comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                comm = Comm(uid[0], world, rank, device=local_rank)
         prob.attach_comm(comm)
     opt = default_options()
 
@@ -427,7 +440,7 @@ def run_ours(args):
                                    f"identity start, full LM solve to Ceres convergence",
                        "sharding": (f"frames by rank, {world} rank(s), 28-double all-reduce per sweep: " +
                                     ("ncclAllReduce between kernels" if args.nccl_allreduce else
-                                     "fused into the sweep kernel (NVLink peer stores + flags, rank-order sum)")) if world > 1 else "single GPU",
+                                     "fused into the sweep kernel (NVLink peer stores, sequence-tagged words, rank-order sum)")) if world > 1 else "single GPU",
                        "l2": f"inputs ({alg_bytes / 1e6:.0f} MB per GPU) larger than the 126 MB L2; roofline leg flushes L2 between launches",
                        "lm": "one fused residual+Jacobian+reduce sweep per LM iteration (speculative Jacobian at the candidate)"},
             "lm_iters_per_s": lm_iters_per_s, "sweeps_per_solve": sweeps / args.steps, "lm_iterations_per_solve": iters / args.steps,

@@ -392,6 +392,14 @@ int finish_create(clc_problem* p) {
     if (p->device < 64) cached_blocks_per_sm[p->device] = blocks_per_sm;
   }
   p->grid = p->num_sms * blocks_per_sm;
+  {
+    // small problems (the reference's own sizes: a few thousand points) do not need the whole machine: a warp takes at
+    // least one 128-point stage, so launch only as many blocks as there are stages to hand out -- fewer tickets and
+    // partial sums on the serial tail of every LM iteration
+    const int64_t stages = (p->n_points + clc::kChunk - 1) / clc::kChunk;
+    const int64_t blocks_needed = std::max<int64_t>(1, (stages + clc::kWarps - 1) / clc::kWarps);
+    if (blocks_needed < p->grid) p->grid = (int)blocks_needed;
+  }
   if (const char* env = std::getenv("CLC_PDL")) p->use_pdl = std::atoi(env) != 0;
   const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
   p->per_warp = std::max<int64_t>(clc::kChunk, round_up((p->n_points + n_warps - 1) / n_warps, clc::kChunk));
@@ -428,19 +436,33 @@ int init_device(clc_problem* p, int device) {
   if (device >= count) return fail(CLC_ERR_INVALID, "device ordinal out of range");
   p->device = device;
   CLC_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CLC_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10)
-    return fail(CLC_ERR_CUDA, std::string("libclc_b200 is built for sm_100a only; device is sm_") +
-                                  std::to_string(prop.major) + std::to_string(prop.minor));
-  p->num_sms = prop.multiProcessorCount;
+  // per-device facts are queried once (cudaGetDeviceProperties alone costs about a millisecond, which would dominate
+  // the reference-sized calls: 50 frames x 180 points solve in 0.25 ms)
+  struct DeviceInfo { bool valid = false; int major = 0, minor = 0, sms = 0; };
+  static std::mutex info_mutex;
+  static DeviceInfo info[64];
+  DeviceInfo di;
   {
+    std::lock_guard<std::mutex> lock(info_mutex);
+    if (device < 64) di = info[device];
+  }
+  if (!di.valid) {
+    CLC_CUDA(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, device));
+    CLC_CUDA(cudaDeviceGetAttribute(&di.minor, cudaDevAttrComputeCapabilityMinor, device));
+    CLC_CUDA(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, device));
     // keep freed device memory in the pool instead of returning it to the driver at every synchronisation
     cudaMemPool_t pool;
     CLC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t threshold = UINT64_MAX;
     CLC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    di.valid = true;
+    std::lock_guard<std::mutex> lock(info_mutex);
+    if (device < 64) info[device] = di;
   }
+  if (di.major < 10)
+    return fail(CLC_ERR_CUDA, std::string("libclc_b200 is built for sm_100a only; device is sm_") + std::to_string(di.major) +
+                                  std::to_string(di.minor));
+  p->num_sms = di.sms;
   CLC_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
   return CLC_OK;
 }
