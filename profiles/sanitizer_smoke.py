@@ -1,0 +1,34 @@
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool memcheck python profiles/sanitizer_smoke.py"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from camlasercalibratool_b200 import Problem  # noqa: E402
+from camlasercalibratool_b200 import formats as fmt  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+x0 = np.array([0, 0, 0, 0, 0, 0, 1.0])
+for edges in (False, True):
+    p = O.generate(60, 150, seed=3, sigma=0.01, exact_m=edges, with_edges=edges)
+    with Problem.from_arrays(p.frame_pose, p.offsets, p.points, p.edge_points) as g:
+        c, H, gr = g.eval(x0)
+        rc, rH, rg = O.evaluate_normal(p, x0)
+        assert abs(c - rc) <= 1e-11 * rc
+        x, s, tr = g.solve(x0)
+        xo, so, _ = O.solve(p, x0)
+        assert O.pose_error(x, xo)[0] < 1e-8 and s.termination == so.termination
+        g.information(x)
+        g.closed_form()
+        g.line_fit()
+        g.download()
+with Problem.synthetic(300, 700, seed=2, sigma=0.01, with_edges=True) as g:  # ragged ends of warp ranges, several blocks
+    x, s, tr = g.solve(x0)
+    g.bench_eval(x, 2, flush_l2=False)
+rng = np.random.default_rng(0)
+ranges = (5 + rng.normal(size=(64, 1081)) * 0.01).astype(np.float32)
+ranges[:, 500:600] = 1.0
+fmt.auto_get_line_segments(ranges, -2.356, 4.712 / 1080, 0.05)
+print("sanitizer smoke ok")
