@@ -42,6 +42,15 @@ class SyntheticDesc(C.Structure):
         ("use_loss", C.c_int),
         ("cauchy_a", C.c_double),
         ("device", C.c_int),
+        ("camera_model", C.c_int),
+        ("camera_intrinsics", C.c_double * 8),
+        ("pixel_sigma", C.c_double),
+        ("image_width", C.c_int),
+        ("image_height", C.c_int),
+        ("grid_rows", C.c_int),
+        ("grid_cols", C.c_int),
+        ("tag_size", C.c_double),
+        ("tag_spacing", C.c_double),
     ]
 
 
@@ -114,6 +123,7 @@ SIGNATURES = {
     "clc_problem_destroy": (C.c_int, [_P]),
     "clc_problem_sizes": (C.c_int, [_P, c_int64_p, c_int64_p, C.POINTER(C.c_int)]),
     "clc_problem_download": (C.c_int, [_P, c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p]),
+    "clc_problem_download_true_poses": (C.c_int, [_P, c_double_p]),
     "clc_eval": (C.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p]),
     "clc_solve_lm": (C.c_int, [_P, c_double_p, C.POINTER(LmOptions), C.POINTER(LmSummary), C.POINTER(LmIteration), C.c_int]),
     "clc_information": (C.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),

@@ -63,6 +63,17 @@ def marshal(obs, use_linefitting_data=True, use_boundary_constraint=False):
     return frame_pose, offsets, np.ascontiguousarray(points), edge
 
 
+# intrinsics of the reference's two shipped configurations
+CAMERA_DEFAULTS = {
+    # config/calibra_config_pinhole.yaml (its distortion block is all zeros; a mild radtan distortion is used instead so that
+    # the undistortion step does something)
+    "radtan": [367.049931000148, 366.94446918887405, 368.7202381120387, 241.13814795878562, -0.05, 0.01, 0.0005, -0.0005],
+    # config/calibra_config.yaml (KANNALA_BRANDT)
+    "equi": [367.049931000148, 366.94446918887405, 368.7202381120387, 241.13814795878562, -0.02276964, -0.00056958, -0.0026224,
+             0.00017455],
+}
+
+
 def default_options(**kw) -> LmOptions:
     o = LmOptions()
     _lib.load().clc_lm_default_options(C.byref(o))
@@ -107,7 +118,11 @@ class Problem:
 
     @classmethod
     def synthetic(cls, n_frames_total, beams, seed=1, sigma=0.0, with_edges=False, frame_begin=0, frame_end=None,
-                  use_loss=True, cauchy_a=0.05, device=-1):
+                  use_loss=True, cauchy_a=0.05, device=-1, camera=None, pixel_sigma=0.0, intrinsics=None,
+                  image_size=(752, 480), grid=(6, 6, 0.055, 0.3)):
+        """camera: None (exact board poses, the reference simulation), "radtan" (pinhole, fx fy cx cy k1 k2 p1 p2) or "equi"
+        (Kannala-Brandt, mu mv u0 v0 k2 k3 k4 k5): the poses handed to the solver are then estimated from noisy corner
+        pixels by the reference's undistort + PnP chain.  Default intrinsics: the reference's config/*.yaml."""
         L = _lib.load()
         d = SyntheticDesc()
         d.n_frames_total = int(n_frames_total)
@@ -115,6 +130,13 @@ class Problem:
         d.frame_end = int(n_frames_total if frame_end is None else frame_end)
         d.beams, d.seed, d.sigma = int(beams), int(seed), float(sigma)
         d.with_edges, d.use_loss, d.cauchy_a, d.device = int(bool(with_edges)), int(bool(use_loss)), float(cauchy_a), int(device)
+        d.camera_model = {None: 0, "none": 0, "radtan": 1, "pinhole": 1, "equi": 2}[camera]
+        if d.camera_model:
+            k = CAMERA_DEFAULTS["radtan" if d.camera_model == 1 else "equi"] if intrinsics is None else intrinsics
+            d.camera_intrinsics = (C.c_double * 8)(*[float(v) for v in k])
+            d.pixel_sigma = float(pixel_sigma)
+            d.image_width, d.image_height = int(image_size[0]), int(image_size[1])
+            d.grid_rows, d.grid_cols, d.tag_size, d.tag_spacing = int(grid[0]), int(grid[1]), float(grid[2]), float(grid[3])
         h = C.c_void_p()
         _lib.check(L.clc_problem_create_synthetic(C.byref(h), C.byref(d)), "clc_problem_create_synthetic")
         return cls(h)
@@ -155,6 +177,12 @@ class Problem:
         _lib.check(self._L.clc_problem_download(self._h, _dp(fp), _ip(off), _dp(pts), _dp(edge), _dp(planes)),
                    "clc_problem_download")
         return dict(frame_pose=fp, offsets=off, points=pts, edge_points=edge, planes=planes)
+
+    def download_true_poses(self):
+        """Synthetic problems with a camera model: the poses the laser points were generated from."""
+        fp = np.empty((self.sizes()[0], 7))
+        _lib.check(self._L.clc_problem_download_true_poses(self._h, _dp(fp)), "clc_problem_download_true_poses")
+        return fp
 
     # ---- the hot path ----
     def eval(self, pose7):

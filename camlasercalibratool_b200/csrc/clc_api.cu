@@ -236,6 +236,7 @@ struct clc_problem {
   // device buffers
   double *x = nullptr, *y = nullptr, *z = nullptr;
   double* frame_pose = nullptr;
+  double* frame_pose_true = nullptr;  // synthetic problems with a camera model: the poses the points were generated from
   double* plane = nullptr;
   int64_t* offsets = nullptr;
   int* warp_first_frame = nullptr;
@@ -534,7 +535,7 @@ int clc_problem_destroy(clc_problem* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->stream) {
-    void* bufs[] = {p->x, p->y, p->z, p->frame_pose, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
+    void* bufs[] = {p->x, p->y, p->z, p->frame_pose, p->frame_pose_true, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
                     p->partials, p->sums, p->pose, p->ticket, p->lm, p->flush_buf, p->p2p_error};
     for (void* b : bufs)
       if (b) cudaFreeAsync(b, p->stream);  // back to the device's memory pool: re-creating a problem is cheap
@@ -639,12 +640,30 @@ int clc_problem_create_synthetic(clc_problem** out, const clc_synthetic_desc* d)
       CLC_CUDA(cudaMallocAsync(&p->edge_plane, sizeof(double) * 4 * p->n_edges, p->stream));
       CLC_CUDA(cudaMallocAsync(&p->edge_pt, sizeof(double) * 3 * p->n_edges, p->stream));
     }
+    clc::CameraDesc cam;
+    cam.model = d->camera_model;
+    for (int k = 0; k < 8; ++k) cam.intr[k] = d->camera_intrinsics[k];
+    cam.pixel_sigma = d->pixel_sigma;
+    cam.grid_rows = d->grid_rows;
+    cam.grid_cols = d->grid_cols;
+    cam.tag_size = d->tag_size;
+    cam.tag_spacing = d->tag_spacing;
+    if (cam.model != clc::kCameraNone) {
+      if (cam.model != clc::kCameraPinholeRadtan && cam.model != clc::kCameraEquidistant)
+        return fail(CLC_ERR_INVALID, "unknown camera_model");
+      if (cam.grid_rows < 1 || cam.grid_cols < 1 || 4 * cam.grid_rows * cam.grid_cols > 256 || !(cam.tag_size > 0.0) ||
+          d->image_width < 1 || d->image_height < 1 || !(cam.intr[0] > 0.0) || !(cam.intr[1] > 0.0))
+        return fail(CLC_ERR_INVALID, "bad camera / grid description");
+      CLC_CUDA(cudaMallocAsync(&p->frame_pose_true, sizeof(double) * 7 * std::max<int64_t>(N, 1), p->stream));
+    }
     if (N > 0) {
-      clc::clc_gen_frames_kernel<<<(unsigned)((N + 127) / 128), 128, 0, p->stream>>>(
-          d->seed, d->frame_begin, N, d->beams, d->with_edges, p->frame_pose, p->offsets, p->edge_pt);
+      clc::clc_gen_frames_kernel<<<(unsigned)((N + 63) / 64), 64, 0, p->stream>>>(
+          d->seed, d->frame_begin, N, d->beams, d->with_edges, cam, d->image_width, d->image_height, p->frame_pose,
+          p->frame_pose_true, p->offsets, p->edge_pt);
       CLC_LAUNCH_CHECK();
       clc::clc_gen_points_kernel<<<(unsigned)N, 256, 0, p->stream>>>(d->seed, d->sigma, d->frame_begin, d->beams,
-                                                                    p->frame_pose, p->x, p->y, p->z);
+                                                                    p->frame_pose_true ? p->frame_pose_true : p->frame_pose,
+                                                                    p->x, p->y, p->z);
       CLC_LAUNCH_CHECK();
     } else {
       CLC_CUDA(cudaMemsetAsync(p->offsets, 0, sizeof(int64_t), p->stream));
@@ -662,6 +681,17 @@ int clc_problem_sizes(const clc_problem* p, int64_t* n_frames, int64_t* n_points
   if (n_frames) *n_frames = p->n_frames;
   if (n_points) *n_points = p->n_points;
   if (has_edges) *has_edges = p->n_edges > 0;
+  return CLC_OK;
+}
+
+int clc_problem_download_true_poses(const clc_problem* p, double* frame_pose_true) {
+  if (!p || !frame_pose_true) return fail(CLC_ERR_INVALID, "NULL argument");
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  if (p->n_frames > 0)
+    CLC_CUDA(cudaMemcpy(frame_pose_true, p->frame_pose_true ? p->frame_pose_true : p->frame_pose,
+                        sizeof(double) * 7 * p->n_frames, cudaMemcpyDeviceToHost));
   return CLC_OK;
 }
 

@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include "clc_camera.cuh"
 #include "clc_expand.cuh"
 #include "clc_lm.cuh"
 
@@ -716,14 +717,29 @@ __global__ void clc_warp_table_kernel(const int64_t* __restrict__ offsets, int64
 // ---- K5: synthetic generator (exact-M mode) ----------------------------------------------------------------------
 
 __global__ void clc_gen_frames_kernel(uint64_t seed, int64_t frame_begin, int64_t n_local, int64_t beams, int with_edges,
-                                      double* __restrict__ frame_pose, int64_t* __restrict__ offsets,
+                                      CameraDesc cam, int image_width, int image_height, double* __restrict__ frame_pose,
+                                      double* __restrict__ frame_pose_true, int64_t* __restrict__ offsets,
                                       double* __restrict__ edge_pt) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) offsets[n_local] = n_local * beams;
   if (i >= n_local) return;
-  double fp[7];
-  gen_frame_pose(seed, frame_begin + i, with_edges != 0, fp);
-  for (int k = 0; k < 7; ++k) frame_pose[i * 7 + k] = fp[k];
+  double fp[7], fe[7];
+  if (cam.model == kCameraNone) {
+    gen_frame_pose(seed, frame_begin + i, with_edges != 0, fp);
+    for (int k = 0; k < 7; ++k) fe[k] = fp[k];
+  } else {
+    // camera mode: the board must be fully in the image; the pose handed to the calibration is the PnP estimate
+    float uv[2 * 256];  // up to 8 x 8 tags
+    const bool in_view = gen_frame_pose_camera(cam, image_width, image_height, seed, frame_begin + i, with_edges != 0, fp);
+    bool ok = in_view && grid_num_corners(cam) <= 256;
+    if (ok) ok = camera_estimate_pose(cam, seed, frame_begin + i, fp, fe, uv);
+    if (!ok)
+      for (int k = 0; k < 7; ++k) fe[k] = fp[k];  // no usable image of the board: fall back to the exact pose
+  }
+  for (int k = 0; k < 7; ++k) {
+    frame_pose[i * 7 + k] = fe[k];
+    if (frame_pose_true != nullptr) frame_pose_true[i * 7 + k] = fp[k];
+  }
   offsets[i] = i * beams;
   if (with_edges) {
     double ep[6];

@@ -64,6 +64,18 @@ typedef struct {
   int use_loss;
   double cauchy_a;
   int device;
+  /* Optional camera measurement chain: the board pose the calibration sees is then ESTIMATED from
+   * noisy corner pixels -- kalibr-grid corners -> Camera::spaceToPlane -> pixel noise -> Camera::liftProjective -> planar
+   * PnP, as reference src/calcCamPose.cpp:279-292,211-236 does with cv::solvePnP -- while the laser hits the true board.
+   * camera_model 0: exact poses (the reference simulation); 1: pinhole + radtan, intrinsics = fx fy cx cy k1 k2 p1 p2
+   * (reference config/calibra_config_pinhole.yaml); 2: equidistant (Kannala-Brandt), intrinsics = mu mv u0 v0 k2 k3 k4 k5
+   * (reference config/calibra_config.yaml).  Boards are redrawn until all grid corners fall inside the image. */
+  int camera_model;
+  double camera_intrinsics[8];
+  double pixel_sigma;     /* std of the corner noise in pixels */
+  int image_width, image_height; /* 752 x 480 in the reference configs */
+  int grid_rows, grid_cols;      /* 6 x 6 */
+  double tag_size, tag_spacing;  /* 0.055 m, 0.3 */
 } clc_synthetic_desc;
 
 /* Ceres Solver::Options subset, defaults = reference src/LaseCamCalCeres.cpp:302-304 + Ceres defaults */
@@ -135,6 +147,8 @@ int clc_problem_destroy(clc_problem* p);
 int clc_problem_sizes(const clc_problem* p, int64_t* n_frames, int64_t* n_points, int* has_edges);
 int clc_problem_download(const clc_problem* p, double* frame_pose, int64_t* offsets, double* points,
                          double* edge_points, double* planes /* [n_frames*4] n,d in the camera frame */);
+/* Synthetic problems with a camera model: the TRUE board poses [n_frames*7] (frame_pose above holds the estimated ones). */
+int clc_problem_download_true_poses(const clc_problem* p, double* frame_pose_true);
 
 /* THE FUSED KERNEL (K1): one sweep over every residual at `pose7` -> H = sum J~^T J~ (row-major 6x6),
  * g = sum J~^T r~, cost = 1/2 sum rho, with the Cauchy correction applied.  All-reduced over the ranks when a

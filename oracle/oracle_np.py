@@ -348,3 +348,95 @@ def auto_get_line_pts(points):
         return None
     best = max(range(len(out)), key=lambda k: (out[k][1] - out[k][0], -k))
     return out[best]
+
+
+# --- camera measurement chain: board corners -> pixels -> normalised points -> PnP ---------------
+# camodocal camera models restated literally (camera_models/src/PinholeCamera.cc, EquidistantCamera.cc); the equidistant
+# back-projection takes the smallest non-negative real root from the companion-matrix eigenvalues (np.roots), exactly
+# as EquidistantCamera.cc:632-734 does.  The PnP is OpenCV itself (cv2.solvePnP), the dependency the reference calls.
+def pinhole_distortion(k, x, y):
+    k1, k2, p1, p2 = k[4:8]
+    rho2 = x * x + y * y
+    rad = k1 * rho2 + k2 * rho2 * rho2
+    return x * rad + 2.0 * p1 * x * y + p2 * (rho2 + 2.0 * x * x), y * rad + 2.0 * p2 * x * y + p1 * (rho2 + 2.0 * y * y)
+
+
+def camera_project(model, k, P):
+    """Camera::spaceToPlane: model 1 = pinhole radtan (fx fy cx cy k1 k2 p1 p2), 2 = equidistant (mu mv u0 v0 k2..k5)."""
+    P = np.asarray(P, dtype=float)
+    if model == 2:
+        theta = np.arccos(P[2] / np.linalg.norm(P))
+        phi = np.arctan2(P[1], P[0])
+        r = theta + k[4] * theta**3 + k[5] * theta**5 + k[6] * theta**7 + k[7] * theta**9
+        return np.array([k[0] * r * np.cos(phi) + k[2], k[1] * r * np.sin(phi) + k[3]])
+    x, y = P[0] / P[2], P[1] / P[2]
+    if any(k[4:8]):
+        dx, dy = pinhole_distortion(k, x, y)
+        x, y = x + dx, y + dy
+    return np.array([k[0] * x + k[2], k[1] * y + k[3]])
+
+
+def camera_lift_normalised(model, k, uv):
+    """Camera::liftProjective followed by the division by z of src/calcCamPose.cpp:290-291."""
+    mx, my = (uv[0] - k[2]) / k[0], (uv[1] - k[3]) / k[1]
+    if model == 2:
+        rn = float(np.hypot(mx, my))
+        phi = 0.0 if rn < 1e-10 else float(np.arctan2(my, mx))
+        coeffs = {1: 1.0, 3: k[4], 5: k[5], 7: k[6], 9: k[7]}
+        npow = 9
+        for kk in (k[7], k[6], k[5], k[4]):
+            if kk == 0.0:
+                npow -= 2
+        if npow == 1:
+            theta = rn
+        else:
+            poly = np.zeros(npow + 1)  # highest power first for np.roots
+            for pw, c in coeffs.items():
+                if pw <= npow:
+                    poly[npow - pw] = c
+            poly[npow] = -rn
+            cands = []
+            for rt in np.roots(poly):
+                if abs(rt.imag) > 1e-10 or rt.real < -1e-10:
+                    continue
+                cands.append(max(rt.real, 0.0))
+            theta = min(cands) if cands else rn
+        return np.array([np.tan(theta) * np.cos(phi), np.tan(theta) * np.sin(phi)])
+    xu, yu = mx, my
+    if any(k[4:8]):
+        dx, dy = pinhole_distortion(k, mx, my)
+        xu, yu = mx - dx, my - dy
+        for _ in range(7):
+            dx, dy = pinhole_distortion(k, xu, yu)
+            xu, yu = mx - dx, my - dy
+    return np.array([xu, yu])
+
+
+def grid_corners(rows, cols, tag_size, tag_spacing):
+    """kalibr april grid, reference src/calcCamPose.cpp:107-136: [4*rows*cols, 2]."""
+    pitch = tag_size * (1.0 + tag_spacing)
+    out = []
+    for tag in range(rows * cols):
+        r, c = divmod(tag, cols)
+        x0, y0 = pitch * c, pitch * r
+        out += [(x0, y0), (x0 + tag_size, y0), (x0 + tag_size, y0 + tag_size), (x0, y0 + tag_size)]
+    return np.array(out)
+
+
+def estimate_pose_cv(model, k, corners_xy, fp_true, pixel_noise=None):
+    """The reference's chain with OpenCV's solvePnP (src/calcCamPose.cpp:211-236,279-292): returns (R_ca, t_ca) estimated."""
+    import cv2
+
+    R = quat_to_rot(fp_true[:4])
+    t = np.asarray(fp_true[4:7], dtype=float)
+    un = []
+    for i, (X, Y) in enumerate(corners_xy):
+        uv = camera_project(model, k, R @ np.array([X, Y, 0.0]) + t)
+        if pixel_noise is not None:
+            uv = uv + pixel_noise[i]
+        un.append(camera_lift_normalised(model, k, uv))
+    p3 = np.c_[corners_xy, np.zeros(len(corners_xy))].astype(np.float32)  # cv::Point3f
+    p2 = np.array(un, dtype=np.float32)                                    # cv::Point2f
+    ok, rvec, tvec = cv2.solvePnP(p3, p2, np.eye(3, dtype=np.float32), np.zeros((1, 5), dtype=np.float32))
+    Rm, _ = cv2.Rodrigues(rvec)
+    return Rm, tvec.ravel(), p2

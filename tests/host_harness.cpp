@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "../camlasercalibratool_b200/csrc/clc_expand.cuh"
+#include "../camlasercalibratool_b200/csrc/clc_camera.cuh"
 #include "../camlasercalibratool_b200/csrc/clc_linefit.cuh"
 #include "../camlasercalibratool_b200/csrc/clc_lm.cuh"
 
@@ -60,6 +61,44 @@ void harness_gen_points(uint64_t seed, double sigma, int64_t frame, int64_t beam
     const double depth = -dl / (cx * nl[0] + sy * nl[1]) + clc::gen_noise(seed, sigma, frame, j);
     pts[3 * j] = depth * cx; pts[3 * j + 1] = depth * sy; pts[3 * j + 2] = 0.0;
   }
+}
+
+// ---- camera measurement chain (clc_camera.cuh) ----
+static clc::CameraDesc make_cam(int model, const double* intr, double sigma, int rows, int cols, double tag, double spacing) {
+  clc::CameraDesc c;
+  c.model = model;
+  for (int k = 0; k < 8; ++k) c.intr[k] = intr[k];
+  c.pixel_sigma = sigma; c.grid_rows = rows; c.grid_cols = cols; c.tag_size = tag; c.tag_spacing = spacing;
+  return c;
+}
+void harness_camera_project(int model, const double* intr, const double* P, double* uv) {
+  clc::camera_project(make_cam(model, intr, 0, 6, 6, 0.055, 0.3), P, uv, uv + 1);
+}
+void harness_camera_lift(int model, const double* intr, const double* uv, double* xy) {
+  clc::camera_lift_normalised(make_cam(model, intr, 0, 6, 6, 0.055, 0.3), uv[0], uv[1], xy, xy + 1);
+}
+void harness_grid_corners(int rows, int cols, double tag, double spacing, double* xy) {
+  const double z[8] = {1, 1, 0, 0, 0, 0, 0, 0};
+  const clc::CameraDesc c = make_cam(1, z, 0, rows, cols, tag, spacing);
+  for (int i = 0; i < clc::grid_num_corners(c); ++i) clc::grid_corner(c, i, xy + 2 * i, xy + 2 * i + 1);
+}
+void harness_pixel_noise(uint64_t seed, double sigma, int64_t frame, int corner, double* n2) {
+  clc::pixel_noise(seed, sigma, frame, corner, n2, n2 + 1);
+}
+int harness_pnp_planar(int n, const double* obj_xy, const double* img_uv, double* R9, double* t3) {
+  auto obj = [&](int i, double* X, double* Y) { *X = obj_xy[2 * i]; *Y = obj_xy[2 * i + 1]; };
+  auto img = [&](int i, double* u, double* v) { *u = img_uv[2 * i]; *v = img_uv[2 * i + 1]; };
+  return clc::pnp_planar(n, obj, img, R9, t3) ? 1 : 0;
+}
+int harness_camera_estimate_pose(int model, const double* intr, double sigma, int rows, int cols, double tag, double spacing,
+                                 uint64_t seed, int64_t frame, const double* fp_true, double* fp_est, float* uv_out) {
+  return clc::camera_estimate_pose(make_cam(model, intr, sigma, rows, cols, tag, spacing), seed, frame, fp_true, fp_est, uv_out) ? 1 : 0;
+}
+
+int harness_gen_frame_pose_camera(int model, const double* intr, int rows, int cols, double tag, double spacing, int width,
+                                  int height, uint64_t seed, int64_t frame, int with_edges, double* fp) {
+  return clc::gen_frame_pose_camera(make_cam(model, intr, 0, rows, cols, tag, spacing), width, height, seed, frame,
+                                    with_edges != 0, fp) ? 1 : 0;
 }
 
 void harness_auto_get_line_pts(const float* ranges, int64_t n, double a0, double inc, double rmin, int* s, int* e) {
