@@ -144,6 +144,8 @@ SIGNATURES = {
     "clc_problem_set_allreduce_mode": (C.c_int, [_P, C.c_int]),
     "clc_bench_eval": (C.c_int, [_P, c_double_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "clc_problem_algorithmic_bytes": (C.c_int, [_P, c_int64_p]),
+    "clc_problem_streamed_bytes": (C.c_int, [_P, c_int64_p]),
+    "clc_problem_set_planar_mode": (C.c_int, [_P, C.c_int]),
     "clc_host_alloc": (C.c_int, [C.POINTER(_P), C.c_int64]),
     "clc_host_free": (C.c_int, [_P]),
     "clc_launch_count": (C.c_int64, []),

@@ -169,6 +169,21 @@ class Problem:
         _lib.check(self._L.clc_problem_algorithmic_bytes(self._h, C.byref(b)), "clc_problem_algorithmic_bytes")
         return b.value
 
+    def streamed_bytes(self):
+        """Bytes one sweep really streams (16 B per point when the planar two-stream kernels are active)."""
+        b = C.c_int64()
+        _lib.check(self._L.clc_problem_streamed_bytes(self._h, C.byref(b)), "clc_problem_streamed_bytes")
+        return b.value
+
+    @property
+    def planar(self):
+        """True if the z stream was dropped (every z exactly 0) and the two-stream kernels run."""
+        return self.streamed_bytes() != self.algorithmic_bytes()
+
+    def set_planar_mode(self, mode):
+        """1 = automatic (default): planar data runs the two-stream kernels; 0 = always the general kernels."""
+        _lib.check(self._L.clc_problem_set_planar_mode(self._h, int(mode)), "clc_problem_set_planar_mode")
+
     def download(self):
         nf, npts, he = self.sizes()
         fp, off, pts = np.empty((nf, 7)), np.empty(nf + 1, dtype=np.int64), np.empty((npts, 3))

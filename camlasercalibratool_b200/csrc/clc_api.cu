@@ -189,6 +189,7 @@ struct PinnedBlock {
   clc::LmState lm;
   double sums[clc::kMaxOut];
   int done;
+  int nonplanar;
 };
 namespace {
 std::mutex g_pinned_mutex;
@@ -263,6 +264,13 @@ struct clc_problem {
   int* p2p_error = nullptr;
   int allreduce_mode = 0;
   int64_t per_warp = 0;
+  int grid_full = 0;  // SM count x resident blocks
+  // planar data (every z exactly 0: a 2-D laser): the z stream is dropped and the two-stream kernels run
+  int* d_nonplanar = nullptr;  // raised by the upload kernel when a z != 0 was seen
+  bool z_all_zero = false;     // property of the data
+  bool planar = false;         // the two-stream kernels are in use (z_all_zero && planar_mode != 0 && large enough)
+  int planar_mode = 1;         // 1 = automatic (default), 0 = always the general three-stream kernels
+  int64_t planar_min_points = 0;
 };
 
 namespace {
@@ -327,12 +335,16 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t le;
+  if (!p->planar && p->z == nullptr) return fail(CLC_ERR_INVALID, "internal: general sweep without a z stream");
   if (mode == clc::kModeClosedForm) {
-    le = cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeClosedForm>, v, a);
+    le = p->planar ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeClosedForm, true>, v, a)
+                   : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeClosedForm, false>, v, a);
   } else if (loss) {
-    le = cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM>, v, a);
+    le = p->planar ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, true>, v, a)
+                   : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, false>, v, a);
   } else {
-    le = cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeLM>, v, a);
+    le = p->planar ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeLM, true>, v, a)
+                   : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeLM, false>, v, a);
   }
   if (le != cudaSuccess) return fail(CLC_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(le));
   CLC_LAUNCH_CHECK();
@@ -356,6 +368,37 @@ int check_p2p_error(clc_problem* p) {
 }
 
 // common tail of the two create paths: planes, warp table, work buffers
+int materialise_z(clc_problem* p);
+
+// Static work partition of the sweep kernels: launch grid, points per warp, first frame of every warp.  Depends on the
+// kernel family (the planar kernels use longer stages), so it is redone when the planar mode changes.
+int partition(clc_problem* p) {
+  const int chunk = p->planar ? clc::kPlanarChunk : clc::kChunk;
+  p->grid = p->grid_full;
+  {
+    // small problems (the reference's own sizes: a few thousand points) do not need the whole machine: a warp takes at
+    // least one stage, so launch only as many blocks as there are stages to hand out -- fewer tickets and
+    // partial sums on the serial tail of every LM iteration
+    const int64_t stages = (p->n_points + chunk - 1) / chunk;
+    const int64_t blocks_needed = std::max<int64_t>(1, (stages + clc::kWarps - 1) / clc::kWarps);
+    if (blocks_needed < p->grid) p->grid = (int)blocks_needed;
+  }
+  const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
+  p->per_warp = std::max<int64_t>(chunk, round_up((p->n_points + n_warps - 1) / n_warps, chunk));
+  if (p->warp_first_frame) CLC_CUDA(cudaFreeAsync(p->warp_first_frame, p->stream));
+  if (p->partials) CLC_CUDA(cudaFreeAsync(p->partials, p->stream));
+  p->warp_first_frame = nullptr;
+  p->partials = nullptr;
+  CLC_CUDA(cudaMallocAsync(&p->warp_first_frame, sizeof(int) * n_warps, p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->partials, sizeof(double) * (size_t)p->grid * clc::kMaxOut, p->stream));
+  const int threads = 256;
+  const int blocks = (int)((n_warps + threads - 1) / threads);
+  clc::clc_warp_table_kernel<<<blocks, threads, 0, p->stream>>>(p->offsets, p->n_frames, p->n_points, p->per_warp, n_warps,
+                                                                p->warp_first_frame);
+  CLC_LAUNCH_CHECK();
+  return CLC_OK;
+}
+
 int finish_create(clc_problem* p) {
   const int threads = 256;
   if (p->n_frames > 0) {
@@ -374,15 +417,15 @@ int finish_create(clc_problem* p) {
   }
   if (blocks_per_sm == 0) {
     int occ = 0, occ_min = 1 << 30;
-    CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<true, clc::kModeLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
-    CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<false, clc::kModeLM>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
-    CLC_CUDA(cudaFuncSetAttribute(clc::clc_sweep_kernel<false, clc::kModeClosedForm>, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
-    CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<true, clc::kModeLM>, clc::kThreads, clc::kDynSmemBytes));
-    occ_min = std::min(occ_min, occ);
-    CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeLM>, clc::kThreads, clc::kDynSmemBytes));
-    occ_min = std::min(occ_min, occ);
-    CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clc::clc_sweep_kernel<false, clc::kModeClosedForm>, clc::kThreads, clc::kDynSmemBytes));
-    occ_min = std::min(occ_min, occ);
+    const void* variants[] = {
+        (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, false>,         (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, true>,
+        (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, false>,        (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, true>,
+        (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, false>, (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, true>};
+    for (const void* fn : variants) {
+      CLC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
+      CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, clc::kThreads, clc::kDynSmemBytes));
+      occ_min = std::min(occ_min, occ);
+    }
     if (occ_min < 1) return fail(CLC_ERR_CUDA, "the sweep kernel does not fit on this device");
     blocks_per_sm = std::max(1, std::min(occ_min, clc::kBlocksPerSM));
     if (const char* env = std::getenv("CLC_BLOCKS_PER_SM")) {
@@ -392,26 +435,8 @@ int finish_create(clc_problem* p) {
     std::lock_guard<std::mutex> lock(cfg_mutex);
     if (p->device < 64) cached_blocks_per_sm[p->device] = blocks_per_sm;
   }
-  p->grid = p->num_sms * blocks_per_sm;
-  {
-    // small problems (the reference's own sizes: a few thousand points) do not need the whole machine: a warp takes at
-    // least one 128-point stage, so launch only as many blocks as there are stages to hand out -- fewer tickets and
-    // partial sums on the serial tail of every LM iteration
-    const int64_t stages = (p->n_points + clc::kChunk - 1) / clc::kChunk;
-    const int64_t blocks_needed = std::max<int64_t>(1, (stages + clc::kWarps - 1) / clc::kWarps);
-    if (blocks_needed < p->grid) p->grid = (int)blocks_needed;
-  }
+  p->grid_full = p->num_sms * blocks_per_sm;
   if (const char* env = std::getenv("CLC_PDL")) p->use_pdl = std::atoi(env) != 0;
-  const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
-  p->per_warp = std::max<int64_t>(clc::kChunk, round_up((p->n_points + n_warps - 1) / n_warps, clc::kChunk));
-  CLC_CUDA(cudaMallocAsync(&p->warp_first_frame, sizeof(int) * n_warps, p->stream));
-  {
-    const int blocks = (int)((n_warps + threads - 1) / threads);
-    clc::clc_warp_table_kernel<<<blocks, threads, 0, p->stream>>>(p->offsets, p->n_frames, p->n_points, p->per_warp,
-                                                                  n_warps, p->warp_first_frame);
-    CLC_LAUNCH_CHECK();
-  }
-  CLC_CUDA(cudaMallocAsync(&p->partials, sizeof(double) * (size_t)p->grid * clc::kMaxOut, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->sums, sizeof(double) * clc::kMaxOut, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->pose, sizeof(double) * 8, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->ticket, sizeof(unsigned int), p->stream));
@@ -425,8 +450,25 @@ int finish_create(clc_problem* p) {
   p->h_sums = p->pinned->sums;
   p->h_done = &p->pinned->done;
   p->h_lm = &p->pinned->lm;
+  p->pinned->nonplanar = 1;
+  CLC_CUDA(cudaMemcpyAsync(&p->pinned->nonplanar, p->d_nonplanar, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
   CLC_CUDA(cudaStreamSynchronize(p->stream));
-  return CLC_OK;
+  p->z_all_zero = p->pinned->nonplanar == 0;
+  if (const char* env = std::getenv("CLC_PLANAR")) p->planar_mode = std::atoi(env) != 0 ? 1 : 0;
+  // The planar kernels stream 256-point stages; they pay off once every warp of the full grid has at least one such stage.
+  // Smaller problems (the reference's own 50 x 180) are latency-bound and keep the 128-point stages of the general kernels.
+  p->planar_min_points = (int64_t)p->grid_full * clc::kWarps * clc::kPlanarChunk;
+  if (const char* env = std::getenv("CLC_PLANAR_MIN_POINTS")) p->planar_min_points = std::atoll(env);
+  p->planar = p->z_all_zero && p->planar_mode != 0 && p->n_points >= p->planar_min_points;
+  if (p->planar && p->z != nullptr) {
+    // a third of the point storage goes back to the pool
+    CLC_CUDA(cudaFreeAsync(p->z, p->stream));
+    p->z = nullptr;
+  } else if (!p->planar) {
+    int rc = materialise_z(p);
+    if (rc != CLC_OK) return rc;
+  }
+  return partition(p);
 }
 
 int init_device(clc_problem* p, int device) {
@@ -468,17 +510,28 @@ int init_device(clc_problem* p, int device) {
   return CLC_OK;
 }
 
-int alloc_points(clc_problem* p) {
-  p->n_points_padded = round_up(p->n_points, clc::kChunk) + clc::kChunk;
+int alloc_points(clc_problem* p, bool with_z) {
+  p->n_points_padded = round_up(p->n_points, clc::kMaxChunk) + clc::kMaxChunk;
   const size_t bytes = sizeof(double) * (size_t)p->n_points_padded;
   CLC_CUDA(cudaMallocAsync(&p->x, bytes, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->y, bytes, p->stream));
-  CLC_CUDA(cudaMallocAsync(&p->z, bytes, p->stream));
+  if (with_z) CLC_CUDA(cudaMallocAsync(&p->z, bytes, p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->d_nonplanar, sizeof(int), p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->d_nonplanar, 0, sizeof(int), p->stream));
   // zero the padding (finite values are required beyond the last point)
   const int64_t tail = p->n_points_padded - p->n_points;
   CLC_CUDA(cudaMemsetAsync(p->x + p->n_points, 0, sizeof(double) * tail, p->stream));
   CLC_CUDA(cudaMemsetAsync(p->y + p->n_points, 0, sizeof(double) * tail, p->stream));
-  CLC_CUDA(cudaMemsetAsync(p->z + p->n_points, 0, sizeof(double) * tail, p->stream));
+  if (with_z) CLC_CUDA(cudaMemsetAsync(p->z + p->n_points, 0, sizeof(double) * tail, p->stream));
+  return CLC_OK;
+}
+
+// all-zero z stream for the general kernels on planar data (clc_problem_set_planar_mode(p, 0))
+int materialise_z(clc_problem* p) {
+  if (p->z != nullptr) return CLC_OK;
+  const size_t bytes = sizeof(double) * (size_t)p->n_points_padded;
+  CLC_CUDA(cudaMallocAsync(&p->z, bytes, p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->z, 0, bytes, p->stream));
   return CLC_OK;
 }
 
@@ -535,7 +588,7 @@ int clc_problem_destroy(clc_problem* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->stream) {
-    void* bufs[] = {p->x, p->y, p->z, p->frame_pose, p->frame_pose_true, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
+    void* bufs[] = {p->x, p->y, p->z, p->d_nonplanar, p->frame_pose, p->frame_pose_true, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
                     p->partials, p->sums, p->pose, p->ticket, p->lm, p->flush_buf, p->p2p_error};
     for (void* b : bufs)
       if (b) cudaFreeAsync(b, p->stream);  // back to the device's memory pool: re-creating a problem is cheap
@@ -570,7 +623,7 @@ int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
   p->use_loss = d->use_loss;
   p->cauchy_a = d->cauchy_a;
   auto body = [&]() -> int {
-    int rc2 = alloc_points(p);
+    int rc2 = alloc_points(p, /*with_z=*/true);
     if (rc2 != CLC_OK) return rc2;
     CLC_CUDA(cudaMallocAsync(&p->frame_pose, sizeof(double) * 7 * std::max<int64_t>(N, 1), p->stream));
     CLC_CUDA(cudaMallocAsync(&p->plane, sizeof(double) * 4 * std::max<int64_t>(N, 1), p->stream));
@@ -597,7 +650,7 @@ int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
         const int64_t n = std::min(chunk, P - b);
         cudaError_t e = cudaMemcpyAsync(stage, d->points + 3 * b, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, p->stream);
         if (e != cudaSuccess) { status = fail(CLC_ERR_CUDA, cudaGetErrorString(e)); break; }
-        clc::clc_aos_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(stage, n, p->x, p->y, p->z, b);
+        clc::clc_aos_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(stage, n, p->x, p->y, p->z, b, p->d_nonplanar);
         g_launches.fetch_add(1);
         e = cudaGetLastError();
         if (e != cudaSuccess) status = fail(CLC_ERR_CUDA, cudaGetErrorString(e));
@@ -631,7 +684,8 @@ int clc_problem_create_synthetic(clc_problem** out, const clc_synthetic_desc* d)
   p->use_loss = d->use_loss;
   p->cauchy_a = d->cauchy_a;
   auto body = [&]() -> int {
-    int rc2 = alloc_points(p);
+    // the simulated laser is two-dimensional (calibr_simulation.cpp:82,88): planar by construction, no z stream
+    int rc2 = alloc_points(p, /*with_z=*/false);
     if (rc2 != CLC_OK) return rc2;
     CLC_CUDA(cudaMallocAsync(&p->frame_pose, sizeof(double) * 7 * std::max<int64_t>(N, 1), p->stream));
     CLC_CUDA(cudaMallocAsync(&p->plane, sizeof(double) * 4 * std::max<int64_t>(N, 1), p->stream));
@@ -699,6 +753,29 @@ int clc_problem_algorithmic_bytes(const clc_problem* p, int64_t* bytes) {
   if (!p || !bytes) return fail(CLC_ERR_INVALID, "NULL argument");
   *bytes = 24 * p->n_points + 40 * p->n_frames + 56 * p->n_edges + 224;
   return CLC_OK;
+}
+
+int clc_problem_streamed_bytes(const clc_problem* p, int64_t* bytes) {
+  if (!p || !bytes) return fail(CLC_ERR_INVALID, "NULL argument");
+  *bytes = (p->planar ? 16 : 24) * p->n_points + 40 * p->n_frames + 56 * p->n_edges + 224;
+  return CLC_OK;
+}
+
+int clc_problem_set_planar_mode(clc_problem* p, int mode) {
+  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
+  if (mode != 0 && mode != 1) return fail(CLC_ERR_INVALID, "planar mode must be 0 or 1");
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  p->planar_mode = mode;
+  const bool planar = p->z_all_zero && mode != 0 && p->n_points >= p->planar_min_points;
+  if (planar == p->planar) return CLC_OK;
+  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  p->planar = planar;
+  if (!p->planar) {
+    rc = materialise_z(p);
+    if (rc != CLC_OK) return rc;
+  }
+  return partition(p);
 }
 
 int clc_problem_download(const clc_problem* p, double* frame_pose, int64_t* offsets, double* points,

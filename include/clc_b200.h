@@ -222,6 +222,17 @@ int clc_problem_set_allreduce_mode(clc_problem* p, int mode);
 int clc_bench_eval(clc_problem* p, const double pose7[7], int n, int flush_l2, float* ms_each);
 /* Algorithmic bytes of one K1 launch on this problem: 24*P + 40*N + 56*edges + 224. */
 int clc_problem_algorithmic_bytes(const clc_problem* p, int64_t* bytes);
+/* Bytes one K1 launch actually streams: the figure above with 16 instead of 24 bytes per point when the planar
+ * (two-stream) kernels are active. */
+int clc_problem_streamed_bytes(const clc_problem* p, int64_t* bytes);
+/* Planar data.  A 2-D laser delivers z == 0 for every point (reference src/utilities.cpp:207, main/calibr_simulation.cpp:82,88,
+ * main/calibr_offline.cpp:141-142) although Oberserve::points is a Vector3d.  The upload detects this; the library then
+ * drops the z stream from HBM and runs two-stream kernels whose results equal the general ones (up to summation order) on such
+ * data (a separate roofline row, 16 B per residual).  mode 1 = automatic (default), 0 = always the
+ * general three-stream kernels (an all-zero z stream is re-materialised if it was dropped).  Problems too small to give
+ * every warp of the grid a 256-point stage (about 6*10^5 points on a B200) are latency-bound and stay on the general
+ * kernels in either mode (environment override for tests: CLC_PLANAR_MIN_POINTS). */
+int clc_problem_set_planar_mode(clc_problem* p, int mode);
 /* Pinned host memory for upload buffers. */
 int clc_host_alloc(void** ptr, int64_t bytes);
 int clc_host_free(void* ptr);

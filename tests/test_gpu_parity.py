@@ -9,6 +9,15 @@ from conftest import pack_sums
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["planar-auto", "general"])
+def sweep_kernel_family(request, monkeypatch):
+    """The generator's laser is two-dimensional (z == 0), which the library detects and serves with its two-stream
+    kernels; every test of this module runs a second time with the general three-stream kernels forced."""
+    monkeypatch.setenv("CLC_PLANAR", "1" if request.param == "planar-auto" else "0")
+    monkeypatch.setenv("CLC_PLANAR_MIN_POINTS", "0")  # also for the small problems, which would otherwise stay general
+    return request.param
+
 X0 = np.array([0, 0, 0, 0, 0, 0, 1.0])
 TOL_SUMS = 1e-11
 TOL_ANG = 1e-6  # rad  (north_star)
@@ -361,3 +370,69 @@ def test_unobservable_configuration_reports_the_null_space(oracle):
     np.testing.assert_allclose(V.T @ V, np.eye(6), atol=1e-12)            # orthonormal
     np.testing.assert_allclose(H @ V, V * sv[None, :], atol=1e-9 * sv[0])  # H v_k = sigma_k v_k
     assert np.abs(H @ V[:, 6 - n_null:]).max() < 1e-7
+
+
+def test_planar_detection_and_bit_identity(oracle, sweep_kernel_family, monkeypatch):
+    """z == 0 everywhere -> the z stream is dropped and the two-stream kernels give the same sums, solves and closed forms
+    (up to the summation order); a single off-plane (or NaN) z keeps the general kernels."""
+    from camlasercalibratool_b200 import Problem
+
+    p = oracle.generate(120, 333, seed=9, sigma=0.01, with_edges=True)
+    x = oracle.pose_plus(oracle.ground_truth()[1], np.array([0.02, -0.01, 0.03, 0.01, -0.02, 0.015]))
+    auto = sweep_kernel_family == "planar-auto"
+    with gpu_problem(p) as g:
+        assert g.planar == auto
+        assert g.algorithmic_bytes() == 24 * p.n_points + 40 * 120 + 56 * 240 + 224
+        assert g.streamed_bytes() == (16 if auto else 24) * p.n_points + 40 * 120 + 56 * 240 + 224
+        g.set_planar_mode(1)
+        assert g.planar
+        a = (g.eval(x), g.solve(x)[0], g.closed_form()[0], g.information(x)[0])
+        g.set_planar_mode(0)
+        assert not g.planar
+        b = (g.eval(x), g.solve(x)[0], g.closed_form()[0], g.information(x)[0])
+        # the same sums up to the summation order (the two families cut the point range into different stages)
+        assert_sums_close(a[0], b[0], tol=1e-13)
+        for u, v in zip(a[1:], b[1:]):
+            np.testing.assert_allclose(u, v, rtol=0, atol=1e-12 * max(1.0, np.abs(v).max()))
+        # each family is deterministic: a second evaluation gives the same bits
+        assert np.array_equal(g.eval(x)[1], b[0][1])
+        g.set_planar_mode(1)
+        assert np.array_equal(g.eval(x)[1], a[0][1])
+        d = g.download()
+        assert np.array_equal(d["points"], p.points)
+    with Problem.synthetic(64, 200, seed=2, sigma=0.01) as g:
+        assert g.planar == auto
+        d = g.download()
+        assert np.all(d["points"][:, 2] == 0.0)
+    # small problems are latency-bound and stay on the general kernels by default
+    monkeypatch.delenv("CLC_PLANAR_MIN_POINTS")
+    with gpu_problem(p) as g:
+        assert not g.planar
+    with Problem.synthetic(700, 1000, seed=2) as g:
+        assert g.planar == auto
+    monkeypatch.setenv("CLC_PLANAR_MIN_POINTS", "0")
+    for bad in (1e-300, np.nan, -1.0):
+        pts = p.points.copy()
+        pts[-1, 2] = bad
+        with Problem.from_arrays(p.frame_pose, p.offsets, pts, p.edge_points) as g:
+            assert not g.planar
+            g.set_planar_mode(1)  # a request, not an override: the data are not planar
+            assert not g.planar
+            assert np.array_equal(g.download()["points"], pts, equal_nan=True)
+
+
+def test_eval_off_plane_points(oracle):
+    """Oberserve::points is a Vector3d: points with z != 0 (a tilted or 3-D scanner) go through the general kernels."""
+    p = oracle.generate(60, 257, seed=13, sigma=0.01, with_edges=True)
+    rng = np.random.default_rng(4)
+    pts = p.points + np.array([0.0, 0.0, 1.0]) * rng.normal(scale=0.3, size=(p.n_points, 1))
+    q = oracle.Problem(p.frame_pose, p.offsets, pts, p.edge_points)
+    with gpu_problem(q) as g:
+        assert not g.planar
+        for x in poses(oracle, 2):
+            assert_sums_close(g.eval(x), oracle.evaluate_normal(q, x))
+        x0 = oracle.pose_plus(oracle.ground_truth()[1], np.array([0.02, -0.01, 0.03, 0.01, -0.02, 0.015]))
+        xs, ss, _ = g.solve(x0)
+        xo, so, _ = oracle.solve(q, x0)
+        ang, dt = oracle.pose_error(xs, xo)
+        assert ang < TOL_ANG and dt < TOL_T and ss.num_iterations == so.num_iterations
