@@ -328,10 +328,12 @@ def run_ours(args):
     except Exception:
         pass
     achieved = alg_bytes / (k_mean * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_planar = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_planar = (tj.get("planar") or {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks, "unit": "GB/s", "frac": achieved / peaks,
@@ -369,7 +371,8 @@ def run_ours(args):
                   "value": total_points * p_sweeps / (p_ms * 1e-3), "unit": UNIT, "ms_per_step": p_ms / args.steps,
                   "lm_iters_per_s": p_iters / (p_ms * 1e-3),
                   "roofline": {"bound": "hbm", "achieved": p_bytes / (pk_mean * 1e-3) / 1e9, "peak": peaks, "unit": "GB/s",
-                               "frac": p_bytes / (pk_mean * 1e-3) / 1e9 / peaks, "kernel": "clc_sweep_kernel<LOSS,LM,PLANAR>",
+                               "frac": p_bytes / (pk_mean * 1e-3) / 1e9 / peaks, "traffic": traffic_planar,
+                               "kernel": "clc_sweep_kernel<LOSS,LM,PLANAR>",
                                "kernel_ms_mean": pk_mean, "kernel_ms_min": float(np.min(pk_ms)),
                                "algorithmic_bytes_per_launch": p_bytes, "residuals_per_s_kernel": n_points / (pk_mean * 1e-3),
                                "speedup_over_24B_kernel": k_mean / pk_mean}}
