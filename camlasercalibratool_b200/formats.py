@@ -115,6 +115,32 @@ def read_result_yaml(path):
     return out
 
 
+# ---- planar.txt / RoiPoints.txt / RoiPtOnLines.txt ------------------------------------------------------------------------
+def save_plane_points(obs, Tcl, path):
+    """reference src/LaseCamCalCeres.cpp:68-110 CalibrationTool_SavePlanePoints: per frame the board plane in the camera
+    frame (``i nx ny nz d`` -> planar.txt) and the laser points / fitted-line points moved into the camera frame by Tcl
+    (``i x y z`` -> RoiPoints.txt, RoiPtOnLines.txt); std::setprecision(3) on a default-format stream = ``%.3g``.
+    The planes come from the library (the same device kernel that feeds the solve)."""
+    from .api import marshal
+
+    Tcl = np.asarray(Tcl, dtype=float)
+    fp, off, pts, _ = marshal(obs, False, False)
+    with Problem.from_arrays(fp, off, pts) as g:
+        planes = g.download()["planes"]
+
+    def g3(v):
+        return "%.3g" % v
+
+    with open(path + "planar.txt", "w") as fa, open(path + "RoiPoints.txt", "w") as fb, open(path + "RoiPtOnLines.txt", "w") as fc:
+        for i, o in enumerate(obs):
+            fa.write(f"{i} " + " ".join(g3(v) for v in planes[i]) + "\n")
+            for f, arr in ((fb, o.points), (fc, o.points_on_line)):
+                arr = np.asarray(arr, dtype=float).reshape(-1, 3)
+                cam = arr @ Tcl[:3, :3].T + Tcl[:3, 3]
+                for q in cam:
+                    f.write(f"{i} " + " ".join(g3(v) for v in q) + "\n")
+
+
 # ---- scans: LaserScan ranges -> points -> board segment ---------------------------------------------------------------
 def scan_to_points(ranges, angle_min, angle_increment, range_min):
     """reference src/utilities.cpp:181-215 TranScanToPoints (host data preparation; invalid beams -> (1000,1000,0))."""

@@ -178,3 +178,33 @@ def test_batched_scan_segments_match_oracle(oracle):
         assert (ref is None and s[k] == -1 and e[k] == -1) or ref == (int(s[k]), int(e[k])), k
     segs = fmt.segments_from_scans(np.arange(2000) * 0.025, ranges, a0, inc, 0.05)
     assert len(segs) == int(np.sum(s >= 0)) and all(len(p) == e[k] - s[k] + 1 for (t, p), k in zip(segs, np.nonzero(s >= 0)[0]))
+
+
+@pytest.mark.gpu
+def test_save_plane_points_files(tmp_path, oracle):
+    """planar.txt / RoiPoints.txt / RoiPtOnLines.txt (reference src/LaseCamCalCeres.cpp:68-110): the plane of every frame
+    is (Tctag^-1)^T (0,0,1,0) and the points are moved by Tcl; three significant digits."""
+    from camlasercalibratool_b200 import Oberserve
+    from camlasercalibratool_b200.formats import save_plane_points
+
+    p = oracle.generate(12, 40, seed=4, sigma=0.01)
+    obs = [Oberserve(p.frame_pose[f, :4].copy(), p.frame_pose[f, 4:].copy(), p.points[p.offsets[f]:p.offsets[f + 1]],
+                     p.points[p.offsets[f]:p.offsets[f + 1]][[0, -1]]) for f in range(p.n_frames)]
+    Tcl = np.linalg.inv(oracle.ground_truth()[0])
+    save_plane_points(obs, Tcl, str(tmp_path) + "/")
+    planar = np.loadtxt(tmp_path / "planar.txt")
+    roi = np.loadtxt(tmp_path / "RoiPoints.txt")
+    lines = np.loadtxt(tmp_path / "RoiPtOnLines.txt")
+    assert planar.shape == (12, 5) and roi.shape == (p.n_points, 4) and lines.shape == (24, 4)
+    assert np.array_equal(planar[:, 0], np.arange(12))
+    for f in range(12):
+        T = np.eye(4)
+        T[:3, :3] = oracle.quat_to_rot(p.frame_pose[f, :4])
+        T[:3, 3] = p.frame_pose[f, 4:]
+        want = np.linalg.inv(T).T @ np.array([0, 0, 1.0, 0])
+        np.testing.assert_allclose(planar[f, 1:], want, rtol=6e-3, atol=6e-3)  # %.3g
+    cam = p.points @ Tcl[:3, :3].T + Tcl[:3, 3]
+    np.testing.assert_allclose(roi[:, 1:], cam, rtol=6e-3, atol=1e-12)
+    assert np.array_equal(roi[:, 0], np.repeat(np.arange(12), np.diff(p.offsets)))
+    for tok in (tmp_path / "planar.txt").read_text().split():
+        assert "%.3g" % float(tok) == tok  # std::setprecision(3), default float format
