@@ -54,6 +54,17 @@ class SyntheticDesc(C.Structure):
     ]
 
 
+class CameraDesc(C.Structure):
+    _fields_ = [
+        ("camera_model", C.c_int),
+        ("intrinsics", C.c_double * 8),
+        ("grid_rows", C.c_int),
+        ("grid_cols", C.c_int),
+        ("tag_size", C.c_double),
+        ("tag_spacing", C.c_double),
+    ]
+
+
 class LmOptions(C.Structure):
     _fields_ = [
         ("max_num_iterations", C.c_int),
@@ -132,6 +143,8 @@ SIGNATURES = {
     "clc_line_fit_points": (C.c_int, [c_double_p, C.c_int64, c_double_p, C.c_int]),
     "clc_scan_segments": (C.c_int, [C.POINTER(C.c_float), C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
+    "clc_estimate_board_poses": (C.c_int, [C.POINTER(CameraDesc), C.c_int64, c_int64_p, C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                           c_double_p, C.POINTER(C.c_int32), C.c_int]),
     "clc_T_to_pose7": (None, [c_double_p, c_double_p]),
     "clc_pose7_to_T": (None, [c_double_p, c_double_p]),
     "clc_shard_range": (C.c_int, [C.c_int64, c_int64_p, C.c_int, C.c_int, c_int64_p, c_int64_p]),

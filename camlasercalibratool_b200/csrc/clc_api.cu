@@ -1077,6 +1077,66 @@ int clc_scan_segments(const float* ranges, int64_t n_scans, int64_t n_beams, dou
   return CLC_OK;
 }
 
+int clc_estimate_board_poses(const clc_camera_desc* cam, int64_t n_frames, const int64_t* det_offsets, const int32_t* tag_ids,
+                             const float* corners_uv, double* pose_wc, int32_t* ok, int device) {
+  if (!cam || n_frames < 0 || !det_offsets || !pose_wc || !ok) return fail(CLC_ERR_INVALID, "bad pose-estimation arguments");
+  if (cam->camera_model != clc::kCameraPinholeRadtan && cam->camera_model != clc::kCameraEquidistant)
+    return fail(CLC_ERR_INVALID, "unknown camera_model");
+  if (cam->grid_rows < 1 || cam->grid_cols < 1 || !(cam->tag_size > 0.0) || !(cam->intrinsics[0] > 0.0) ||
+      !(cam->intrinsics[1] > 0.0))
+    return fail(CLC_ERR_INVALID, "bad camera / grid description");
+  if (n_frames == 0) return CLC_OK;
+  if (det_offsets[0] != 0) return fail(CLC_ERR_INVALID, "det_offsets[0] must be 0");
+  for (int64_t f = 0; f < n_frames; ++f)
+    if (det_offsets[f + 1] < det_offsets[f]) return fail(CLC_ERR_INVALID, "det_offsets must be non-decreasing");
+  const int64_t D = det_offsets[n_frames];
+  if (D > 0 && (!tag_ids || !corners_uv)) return fail(CLC_ERR_INVALID, "detections missing");
+  int count = 0;
+  CLC_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0) CLC_CUDA(cudaGetDevice(&device));
+  if (device >= count) return fail(CLC_ERR_INVALID, "device ordinal out of range");
+  CLC_CUDA(cudaSetDevice(device));
+  clc::CameraDesc c;
+  c.model = cam->camera_model;
+  for (int k = 0; k < 8; ++k) c.intr[k] = cam->intrinsics[k];
+  c.pixel_sigma = 0.0;
+  c.grid_rows = cam->grid_rows;
+  c.grid_cols = cam->grid_cols;
+  c.tag_size = cam->tag_size;
+  c.tag_spacing = cam->tag_spacing;
+  int64_t* d_off = nullptr;
+  int *d_ids = nullptr, *d_ok = nullptr;
+  float *d_uv = nullptr, *d_lift = nullptr;
+  double* d_pose = nullptr;
+  cudaStream_t st;
+  CLC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  const size_t Dm = (size_t)std::max<int64_t>(D, 1);
+  cudaError_t e = cudaMallocAsync(&d_off, sizeof(int64_t) * (n_frames + 1), st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_ids, sizeof(int) * Dm, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_uv, sizeof(float) * 8 * Dm, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_lift, sizeof(float) * 8 * Dm, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_pose, sizeof(double) * 7 * n_frames, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_ok, sizeof(int) * n_frames, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, det_offsets, sizeof(int64_t) * (n_frames + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && D > 0) e = cudaMemcpyAsync(d_ids, tag_ids, sizeof(int) * D, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && D > 0) e = cudaMemcpyAsync(d_uv, corners_uv, sizeof(float) * 8 * D, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    clc::clc_estimate_poses_kernel<<<(unsigned)((n_frames + 63) / 64), 64, 0, st>>>(c, n_frames, d_off, d_ids, d_uv, d_lift, d_pose, d_ok);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pose_wc, d_pose, sizeof(double) * 7 * n_frames, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ok, d_ok, sizeof(int) * n_frames, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  void* bufs[] = {d_off, d_ids, d_uv, d_lift, d_pose, d_ok};
+  for (void* b : bufs)
+    if (b) cudaFreeAsync(b, st);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (e != cudaSuccess) return fail(CLC_ERR_CUDA, cudaGetErrorString(e));
+  return CLC_OK;
+}
+
 // ---- multi-GPU --------------------------------------------------------------------------------------------------
 
 int clc_shard_range(int64_t n_frames, const int64_t* offsets, int nranks, int rank, int64_t* begin, int64_t* end) {

@@ -397,4 +397,61 @@ CLC_HD bool camera_estimate_pose(const CameraDesc& cam, uint64_t seed, int64_t f
   return true;
 }
 
+// ---- pose of the board from its detected tag corners (reference src/calcCamPose.cpp:270-294 calcCamPose after
+//      FindTargetCorner, and :211-236 EstimatePose) --------------------------------------------------------------------
+// One frame: n_det detected tags, ascending id (:78-79), corners[n_det*4*2] float pixel coordinates in the detector's
+// corner order (:64-70).  Every corner is undistorted onto the normalised image plane (liftProjective, x/z y/z, stored as
+// cv::Point2f), paired with its kalibr-grid object point (cv::Point3f, :114-136; a single tag of id 0 is the APRILTAG
+// pattern :160-178), and solvePnP with identity intrinsics gives T_cw; the function returns T_wc = T_cw^-1 (:229-230)
+// as pose_wc = (qx, qy, qz, qw, x, y, z) -- what kalibratag_detector_node writes to apriltag_pose.txt.
+// false (and the identity pose, :216-220) for fewer than 4 points, a tag id outside the grid, or a failed PnP.
+CLC_HD bool estimate_pose_from_detections(const CameraDesc& cam, int n_det, const int* tag_ids, const float* corners,
+                                          float* lifted /* scratch [n_det*8] */, double* pose_wc) {
+  pose_wc[0] = pose_wc[1] = pose_wc[2] = 0.0;
+  pose_wc[3] = 1.0;
+  pose_wc[4] = pose_wc[5] = pose_wc[6] = 0.0;
+  const int n = 4 * n_det;
+  if (n < 4) return false;
+  const int n_tags = cam.grid_rows * cam.grid_cols;
+  for (int d = 0; d < n_det; ++d)
+    if (tag_ids[d] < 0 || tag_ids[d] >= n_tags) return false;
+  for (int i = 0; i < n; ++i) {
+    double xn, yn;
+    camera_lift_normalised(cam, (double)corners[2 * i], (double)corners[2 * i + 1], &xn, &yn);
+    lifted[2 * i] = (float)xn;
+    lifted[2 * i + 1] = (float)yn;
+  }
+  auto obj = [&](int i, double* X, double* Y) {
+    double x, y;
+    grid_corner(cam, tag_ids[i >> 2] * 4 + (i & 3), &x, &y);
+    *X = (double)(float)x;
+    *Y = (double)(float)y;
+  };
+  auto img = [&](int i, double* u, double* v) {
+    *u = (double)lifted[2 * i];
+    *v = (double)lifted[2 * i + 1];
+  };
+  double Rcw[9], tcw[3];
+  if (!pnp_planar(n, obj, img, Rcw, tcw)) return false;
+  const double Rwc[9] = {Rcw[0], Rcw[3], Rcw[6], Rcw[1], Rcw[4], Rcw[7], Rcw[2], Rcw[5], Rcw[8]};
+  rot_to_quat(Rwc, pose_wc);
+  for (int r = 0; r < 3; ++r) pose_wc[4 + r] = -(Rwc[3 * r] * tcw[0] + Rwc[3 * r + 1] * tcw[1] + Rwc[3 * r + 2] * tcw[2]);
+  return true;
+}
+
+#ifdef __CUDACC__
+// one thread per frame (the PnP refinement is sequential; the batch is the parallelism)
+__global__ void clc_estimate_poses_kernel(CameraDesc cam, int64_t n_frames, const int64_t* __restrict__ det_offsets,
+                                          const int* __restrict__ tag_ids, const float* __restrict__ corners,
+                                          float* __restrict__ lifted, double* __restrict__ pose_wc, int* __restrict__ ok) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_frames) return;
+  const int64_t d0 = det_offsets[i], d1 = det_offsets[i + 1];
+  double pose[7];
+  const bool good = estimate_pose_from_detections(cam, (int)(d1 - d0), tag_ids + d0, corners + 8 * d0, lifted + 8 * d0, pose);
+  for (int k = 0; k < 7; ++k) pose_wc[i * 7 + k] = pose[k];
+  ok[i] = good ? 1 : 0;
+}
+#endif
+
 }  // namespace clc

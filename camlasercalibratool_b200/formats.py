@@ -115,6 +115,44 @@ def read_result_yaml(path):
     return out
 
 
+# ---- board poses from tag detections (the arithmetic of kalibratag_detector_node) ---------------------------------------
+def estimate_board_poses(camera, detections, intrinsics=None, grid=(6, 6, 0.055, 0.3), device=-1):
+    """Batched CamPoseEst::calcCamPose minus the tag detector (reference src/calcCamPose.cpp:270-294, :211-236) on the
+    GPU.  ``camera``: "radtan" | "equi"; ``detections``: per frame a pair (tag_ids[k], corners[k,4,2] pixel coordinates)
+    in ascending id order, as the AprilTag detector of the reference delivers them.  Returns (pose_wc[n,7] =
+    qx qy qz qw x y z of T_wc, ok[n] bool); frames with fewer than 4 points or a bad id get the identity pose, ok False."""
+    import ctypes as C
+
+    from . import _lib
+    from .api import CAMERA_DEFAULTS
+
+    d = _lib.CameraDesc()
+    d.camera_model = {"radtan": 1, "pinhole": 1, "equi": 2}[camera]
+    k = CAMERA_DEFAULTS["radtan" if d.camera_model == 1 else "equi"] if intrinsics is None else intrinsics
+    d.intrinsics = (C.c_double * 8)(*[float(v) for v in k])
+    d.grid_rows, d.grid_cols, d.tag_size, d.tag_spacing = int(grid[0]), int(grid[1]), float(grid[2]), float(grid[3])
+    n = len(detections)
+    counts = [len(np.atleast_1d(ids)) for ids, _ in detections]
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    ids = np.ascontiguousarray(np.concatenate([np.atleast_1d(i) for i, _ in detections]) if n else [], dtype=np.int32)
+    uv = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float32).reshape(-1, 8) for _, c in detections])
+                              if n else np.zeros((0, 8)), dtype=np.float32)
+    pose = np.zeros((n, 7))
+    ok = np.zeros(n, dtype=np.int32)
+    _lib.check(_lib.load().clc_estimate_board_poses(C.byref(d), n, off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                    ids.ctypes.data_as(C.POINTER(C.c_int32)), uv.ctypes.data_as(C.POINTER(C.c_float)),
+                                                    pose.ctypes.data_as(C.POINTER(C.c_double)), ok.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    int(device)), "clc_estimate_board_poses")
+    return pose, ok.astype(bool)
+
+
+def cam_poses_from_detections(timestamps, camera, detections, **kw) -> list[CamPose]:
+    """reference main/kalibratag_detector_node.cpp:206-234: the CamPose list (frames without a usable detection dropped)
+    that save_cam_pose_txt writes as apriltag_pose.txt."""
+    pose, ok = estimate_board_poses(camera, detections, **kw)
+    return [CamPose(float(t), pose[i, :4].copy(), pose[i, 4:].copy()) for i, t in enumerate(timestamps) if ok[i]]
+
+
 # ---- planar.txt / RoiPoints.txt / RoiPtOnLines.txt ------------------------------------------------------------------------
 def save_plane_points(obs, Tcl, path):
     """reference src/LaseCamCalCeres.cpp:68-110 CalibrationTool_SavePlanePoints: per frame the board plane in the camera

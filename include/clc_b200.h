@@ -189,6 +189,24 @@ int clc_line_fit_points(const double* points_xyz, int64_t n, double line[2], int
 int clc_scan_segments(const float* ranges, int64_t n_scans, int64_t n_beams, double angle_min, double angle_increment,
                       double range_min, int32_t* seg_start, int32_t* seg_end, int device);
 
+/* Board poses from detected tag corners, batched: the arithmetic of CamPoseEst::calcCamPose after the tag detector
+ * (reference src/calcCamPose.cpp:270-294: liftProjective of every corner, x/z y/z as cv::Point2f) and of
+ * CamPoseEst::EstimatePose (:211-236: solvePnP with identity intrinsics on the kalibr-grid object points :114-136,
+ * T_wc = T_cw^-1) -- what main/kalibratag_detector_node.cpp turns into apriltag_pose.txt.  No image processing.
+ * camera_model 1 = pinhole + radtan (fx fy cx cy k1 k2 p1 p2), 2 = equidistant / Kannala-Brandt (mu mv u0 v0 k2 k3 k4 k5).
+ * Frame f owns detections det_offsets[f] .. det_offsets[f+1] (ascending tag id); corners_uv[D*8] = 4 corners (u, v) per
+ * detection in detector order.  pose_wc[n_frames*7] = (qx qy qz qw x y z) of T_wc; ok[f] = 0 (identity pose) for fewer
+ * than 4 points, a tag id outside the grid or a degenerate configuration. */
+typedef struct clc_camera_desc {
+  int camera_model;
+  double intrinsics[8];
+  int grid_rows, grid_cols; /* april grid; a single tag is a 1 x 1 grid */
+  double tag_size;          /* metres */
+  double tag_spacing;       /* gap / tag_size (kalibr convention) */
+} clc_camera_desc;
+int clc_estimate_board_poses(const clc_camera_desc* cam, int64_t n_frames, const int64_t* det_offsets, const int32_t* tag_ids,
+                             const float* corners_uv, double* pose_wc, int32_t* ok, int device);
+
 /* Eigen-equivalent conversions used on both sides of the boundary (reference :215-219 and :311-314). */
 void clc_T_to_pose7(const double T16[16], double pose7[7]);
 void clc_pose7_to_T(const double pose7[7], double T16[16]);

@@ -2,6 +2,7 @@
 // runs -- the LM state machine, the moment expansion, the plane and generator math -- can be checked against the
 // oracle on a machine without a GPU.  Never shipped, never linked into libclc_b200.so.
 #include <cstring>
+#include <vector>
 
 #include "../camlasercalibratool_b200/csrc/clc_expand.cuh"
 #include "../camlasercalibratool_b200/csrc/clc_camera.cuh"
@@ -99,6 +100,13 @@ int harness_gen_frame_pose_camera(int model, const double* intr, int rows, int c
                                   int height, uint64_t seed, int64_t frame, int with_edges, double* fp) {
   return clc::gen_frame_pose_camera(make_cam(model, intr, 0, rows, cols, tag, spacing), width, height, seed, frame,
                                     with_edges != 0, fp) ? 1 : 0;
+}
+
+int harness_estimate_pose_from_detections(int model, const double* intr, int rows, int cols, double tag, double spacing, int n_det,
+                                          const int* ids, const float* corners, double* pose_wc) {
+  std::vector<float> lifted(8 * (size_t)(n_det > 0 ? n_det : 1));
+  return clc::estimate_pose_from_detections(make_cam(model, intr, 0, rows, cols, tag, spacing), n_det, ids, corners,
+                                            lifted.data(), pose_wc) ? 1 : 0;
 }
 
 void harness_auto_get_line_pts(const float* ranges, int64_t n, double a0, double inc, double rmin, int* s, int* e) {

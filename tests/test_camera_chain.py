@@ -214,3 +214,89 @@ def test_device_generator_camera_without_pixel_noise_recovers_the_true_poses(ora
     # without a camera the true poses are the poses
     with Problem.synthetic(20, 16, seed=3) as g:
         assert np.array_equal(g.download()["frame_pose"], g.download_true_poses())
+
+
+# ---- board poses from tag detections (calcCamPose minus the detector) ---------------------------------------------------
+def _synthetic_detections(oracle_np, model, k, rng, n_frames, sigma=0.15):
+    """Per frame: a random subset of the 36 tags (ascending id), their 4 corners projected and disturbed, as float32."""
+    corners = oracle_np.grid_corners(*GRID)[:, :2].reshape(36, 4, 2)
+    out, truth = [], []
+    for _ in range(n_frames):
+        fp = random_board_pose(rng)
+        R, t = oracle_np.quat_to_rot(fp[:4]), fp[4:]
+        ids = np.sort(rng.choice(36, size=rng.integers(1, 37), replace=False)).astype(np.int32)
+        uv = np.array([[oracle_np.camera_project(model, k, R @ np.array([X, Y, 0.0]) + t) for X, Y in corners[i]] for i in ids])
+        out.append((ids, (uv + rng.normal(scale=sigma, size=uv.shape)).astype(np.float32)))
+        truth.append(fp)
+    return out, truth, corners
+
+
+def _pose_cv(oracle_np, cv2, model, k, ids, uv, corners):
+    p2 = np.array([oracle_np.camera_lift_normalised(model, k, p.astype(float)) for p in uv.reshape(-1, 2)], dtype=np.float32)
+    p3 = np.c_[corners[ids].reshape(-1, 2), np.zeros(4 * len(ids))].astype(np.float32)
+    _, rvec, tvec = cv2.solvePnP(p3, p2, np.eye(3, dtype=np.float32), np.zeros((1, 5), dtype=np.float32))
+    Rcw, _ = cv2.Rodrigues(rvec)
+    return Rcw.T, -Rcw.T @ tvec.ravel()  # T_wc (src/calcCamPose.cpp:229-230)
+
+
+@pytest.mark.parametrize("model,k", [(1, PINHOLE), (2, EQUI)])
+def test_pose_from_detections_matches_opencv(harness, oracle_np, model, k):
+    cv2 = pytest.importorskip("cv2")
+    L = _bind(harness)
+    L.harness_estimate_pose_from_detections.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double,
+                                                        C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    rng = np.random.default_rng(8)
+    dets, truth, corners = _synthetic_detections(oracle_np, model, k, rng, 25)
+    for (ids, uv), fp in zip(dets, truth):
+        pose = np.empty(7)
+        ok = L.harness_estimate_pose_from_detections(model, _d(k), 6, 6, 0.055, 0.3, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     np.ascontiguousarray(uv).ctypes.data_as(C.POINTER(C.c_float)), _d(pose))
+        assert ok == 1
+        Rwc, twc = _pose_cv(oracle_np, cv2, model, k, ids, uv, corners)
+        Re = oracle_np.quat_to_rot(pose[:4])
+        ang = np.arccos(np.clip((np.trace(Re.T @ Rwc) - 1) / 2, -1, 1))
+        # a single tag (4 points, 5.5 cm) is poorly conditioned: OpenCV's own iteration stops at ~1e-4 there
+        tol = 3e-5 if len(ids) >= 4 else 2e-3
+        assert ang < tol and np.linalg.norm(pose[4:] - twc) < tol * 5, (len(ids), ang)
+    # error convention: fewer than 4 points, or an id outside the grid -> false and the identity pose
+    pose = np.empty(7)
+    ids = np.array([40], dtype=np.int32)
+    uv = np.zeros(8, dtype=np.float32)
+    for n_det in (0, 1):
+        assert L.harness_estimate_pose_from_detections(model, _d(k), 6, 6, 0.055, 0.3, n_det, ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       uv.ctypes.data_as(C.POINTER(C.c_float)), _d(pose)) == 0
+        assert np.array_equal(pose, [0, 0, 0, 1, 0, 0, 0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("camera,model,k", [("radtan", 1, PINHOLE), ("equi", 2, EQUI)])
+def test_batched_board_poses_match_the_host_build(harness, oracle_np, tmp_path, camera, model, k):
+    from camlasercalibratool_b200.formats import cam_poses_from_detections, estimate_board_poses, load_cam_pose_txt, save_cam_pose_txt
+
+    L = _bind(harness)
+    L.harness_estimate_pose_from_detections.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double, C.c_double,
+                                                        C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)]
+    rng = np.random.default_rng(11)
+    dets, truth, _ = _synthetic_detections(oracle_np, model, k, rng, 300)
+    dets[7] = (np.zeros(0, dtype=np.int32), np.zeros((0, 4, 2), dtype=np.float32))   # nothing detected
+    dets[9] = (np.array([36], dtype=np.int32), np.zeros((1, 4, 2), dtype=np.float32))  # id outside the 6 x 6 grid
+    pose, ok = estimate_board_poses(camera, dets, intrinsics=k)
+    assert not ok[7] and not ok[9] and ok.sum() == 298
+    assert np.array_equal(pose[7], [0, 0, 0, 1, 0, 0, 0])
+    for i, (ids, uv) in enumerate(dets):
+        want = np.empty(7)
+        good = L.harness_estimate_pose_from_detections(model, _d(k), 6, 6, 0.055, 0.3, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       np.ascontiguousarray(uv).ctypes.data_as(C.POINTER(C.c_float)), _d(want))
+        assert bool(good) == bool(ok[i])
+        tol = 2e-6 if len(ids) >= 4 else 1e-4
+        np.testing.assert_allclose(pose[i], want, rtol=0, atol=tol)
+        if ok[i] and len(ids) >= 9:  # T_wc is the inverse of the board pose the pixels were made from
+            Rca = oracle_np.quat_to_rot(truth[i][:4])
+            assert np.abs(oracle_np.quat_to_rot(pose[i, :4]) - Rca.T).max() < 0.05
+            assert np.abs(pose[i, 4:] + Rca.T @ truth[i][4:]).max() < 0.05
+    # and on to apriltag_pose.txt, as the detector node does
+    cams = cam_poses_from_detections(np.arange(300) * 0.05, camera, dets, intrinsics=k)
+    assert len(cams) == 298
+    save_cam_pose_txt(tmp_path / "apriltag_pose.txt", cams)
+    back = load_cam_pose_txt(tmp_path / "apriltag_pose.txt")
+    assert len(back) == 298 and abs(back[8].timestamp - 0.5) < 1e-9  # frames 7 and 9 were dropped
