@@ -265,6 +265,7 @@ struct clc_problem {
   int allreduce_mode = 0;
   int64_t per_warp = 0;
   int grid_full = 0;  // SM count x resident blocks
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // device time of clc_solve_lm
   // planar data (every z exactly 0: a 2-D laser): the z stream is dropped and the two-stream kernels run
   int* d_nonplanar = nullptr;  // raised by the upload kernel when a z != 0 was seen
   bool z_all_zero = false;     // property of the data
@@ -595,6 +596,8 @@ int clc_problem_destroy(clc_problem* p) {
     cudaStreamSynchronize(p->stream);
     cudaStreamDestroy(p->stream);
   }
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
   pinned_release(p->pinned);
   delete p;
   return CLC_OK;
@@ -940,9 +943,9 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
   if (opt.iterations_per_sync < 1) opt.iterations_per_sync = 1;
 
   clc::lm_init(&p->h_lm->core, pose7, opt);
-  cudaEvent_t ev0, ev1;
-  CLC_CUDA(cudaEventCreate(&ev0));
-  CLC_CUDA(cudaEventCreate(&ev1));
+  if (!p->ev0) CLC_CUDA(cudaEventCreate(&p->ev0));  // kept for the life of the problem (destroyed with it)
+  if (!p->ev1) CLC_CUDA(cudaEventCreate(&p->ev1));
+  cudaEvent_t ev0 = p->ev0, ev1 = p->ev1;
   CLC_CUDA(cudaMemcpyAsync(&p->lm->core, &p->h_lm->core, sizeof(clc::LmCore), cudaMemcpyHostToDevice, p->stream));
   CLC_CUDA(cudaEventRecord(ev0, p->stream));
   const bool fused_update = (p->nranks <= 1) || p->allreduce_mode == 1;
@@ -976,8 +979,6 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
   CLC_CUDA(cudaStreamSynchronize(p->stream));
   float ms = 0.f;
   CLC_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   rc = check_p2p_error(p);
   if (rc != CLC_OK) return rc;
 
@@ -1011,18 +1012,20 @@ int clc_problem_line_fit(clc_problem* p, double* lines, int max_num_iterations, 
   const int64_t N = p->n_frames;
   if (N == 0) return CLC_OK;
   double *d_lines = nullptr, *d_info = nullptr;
-  CLC_CUDA(cudaMallocAsync(&d_lines, sizeof(double) * 2 * N, p->stream));
-  if (info) CLC_CUDA(cudaMallocAsync(&d_info, sizeof(double) * 4 * N, p->stream));
-  CLC_CUDA(cudaMemcpyAsync(d_lines, lines, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, p->stream));
-  const int warps = 8;
-  clc::clc_line_fit_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, p->stream>>>(
-      p->x, p->y, p->offsets, N, max_num_iterations, p->cauchy_a, d_lines, d_info);
-  g_launches.fetch_add(1);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = cudaMallocAsync(&d_lines, sizeof(double) * 2 * N, p->stream);
+  if (e == cudaSuccess && info) e = cudaMallocAsync(&d_info, sizeof(double) * 4 * N, p->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_lines, lines, sizeof(double) * 2 * N, cudaMemcpyHostToDevice, p->stream);
+  if (e == cudaSuccess) {
+    const int warps = 8;
+    clc::clc_line_fit_kernel<<<(unsigned)((N + warps - 1) / warps), warps * 32, 0, p->stream>>>(
+        p->x, p->y, p->offsets, N, max_num_iterations, p->cauchy_a, d_lines, d_info);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
   if (e == cudaSuccess) e = cudaMemcpyAsync(lines, d_lines, sizeof(double) * 2 * N, cudaMemcpyDeviceToHost, p->stream);
   if (e == cudaSuccess && info) e = cudaMemcpyAsync(info, d_info, sizeof(double) * 4 * N, cudaMemcpyDeviceToHost, p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
-  cudaFreeAsync(d_lines, p->stream);
+  if (d_lines) cudaFreeAsync(d_lines, p->stream);
   if (d_info) cudaFreeAsync(d_info, p->stream);
   if (e != cudaSuccess) return fail(CLC_ERR_CUDA, cudaGetErrorString(e));
   return CLC_OK;
