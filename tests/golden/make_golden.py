@@ -5,6 +5,11 @@ ROS), so these fixtures are produced by the two independent restatements of the 
   * factor_kat.json   : residual + 1x6 Jacobian of PointInPlaneFactor for hand-checkable inputs, derived with sympy
                         by differentiating n.(R(q (x) dq(dtheta)) p + t + dt) + d symbolically (independent of both
                         oracles' analytic Jacobians).
+  * preprocessing.json: eight LaserScan-like range arrays (self-contained float32 inputs) -> board segment indices
+                        (AutoGetLinePts) and the robust line fit of the segment (LineFittingCeres), numpy twin.
+  * camera_chain.json : both camera models: 3-D points -> pixels, pixels -> normalised image plane (np.roots for the
+                        Kannala-Brandt back-projection), and tag detections -> T_wc by OpenCV's solvePnP itself
+                        (the library the reference calls at src/calcCamPose.cpp:225).
   * config1_seed*.json: BASELINE config 1 (50 frames x 180 beams, faithful ragged generator, 1 cm range noise):
                         generator outputs, (cost, H, g) at the identity start and at ground truth, the full LM
                         trajectory and result, closed form, analysis tail -- computed with the numpy twin
@@ -94,7 +99,78 @@ def config1(seed):
     return out
 
 
+def preprocessing():
+    from oracle import oracle_np as N
+
+    rng = np.random.default_rng(17)
+    n_beams = 1081
+    a0, inc = -2.356, 4.712 / (n_beams - 1)
+    ang = a0 + np.arange(n_beams) * inc
+    scans = []
+    for k in range(8):
+        r = (5 + np.sin(ang * 3 + rng.uniform(0, 6)) * 1.5 + rng.normal(size=n_beams) * 0.01).astype(np.float32)
+        if k % 4 != 3:
+            c, w, d = rng.uniform(-0.6, 0.6), rng.uniform(0.15, 0.35), rng.uniform(0.6, 1.5)
+            m = np.abs(ang - c) < w
+            r[m] = (d / np.cos(ang[m] - c) + rng.normal(size=int(m.sum())) * 0.003).astype(np.float32)
+        r[rng.random(n_beams) < 0.01] = np.inf
+        pts = N.scan_to_points(r, a0, inc, 0.05)
+        seg = N.auto_get_line_pts(pts)
+        entry = dict(ranges=[float(v) if np.isfinite(v) else "inf" for v in r], segment=None if seg is None else list(seg))
+        if seg is not None:
+            line, term, trace = N.line_fit(pts[seg[0]:seg[1] + 1])
+            entry["line"] = [float(v) for v in line]
+            entry["line_termination"] = term
+            entry["line_iterations"] = len(trace)
+            entry["point_first"] = pts[seg[0]].tolist()
+        scans.append(entry)
+    return dict(angle_min=a0, angle_increment=inc, range_min=0.05, scans=scans)
+
+
+def camera_chain():
+    import cv2
+
+    from oracle import oracle_np as N
+
+    rng = np.random.default_rng(23)
+    out = {}
+    models = {"radtan": (1, [367.05, 366.94, 368.72, 241.14, -0.28, 0.07, 0.0003, -0.0002]),
+              "equi": (2, [363.0, 363.2, 370.1, 240.3, -0.013, 0.021, -0.034, 0.012])}
+    grid = (6, 6, 0.055, 0.3)
+    corners = N.grid_corners(*grid)[:, :2].reshape(36, 4, 2)
+    for name, (model, k) in models.items():
+        k = np.array(k)
+        P = np.c_[rng.uniform(-0.8, 0.8, 12), rng.uniform(-0.6, 0.6, 12), rng.uniform(0.5, 3.0, 12)]
+        P = P[np.hypot(P[:, 0], P[:, 1]) / P[:, 2] < 0.4]  # where the 8-step radtan recursion has converged
+        uv = np.array([N.camera_project(model, k, p) for p in P])
+        lift = np.array([N.camera_lift_normalised(model, k, q) for q in uv])
+        frames = []
+        for _ in range(6):
+            ax = rng.normal(size=3)
+            ax /= np.linalg.norm(ax)
+            a = rng.uniform(0, 0.6)
+            q = np.concatenate([ax * np.sin(a / 2), [np.cos(a / 2)]])
+            t = np.array([rng.uniform(-0.4, 0.1), rng.uniform(-0.35, 0.05), rng.uniform(0.5, 2.0)])
+            R = N.quat_to_rot(q)
+            ids = np.sort(rng.choice(36, size=int(rng.integers(6, 37)), replace=False))
+            pix = np.array([[N.camera_project(model, k, R @ np.array([X, Y, 0.0]) + t) for X, Y in corners[i]] for i in ids])
+            pix = (pix + rng.normal(scale=0.15, size=pix.shape)).astype(np.float32)
+            p2 = np.array([N.camera_lift_normalised(model, k, c.astype(float)) for c in pix.reshape(-1, 2)], dtype=np.float32)
+            p3 = np.c_[corners[ids].reshape(-1, 2), np.zeros(4 * len(ids))].astype(np.float32)
+            _, rvec, tvec = cv2.solvePnP(p3, p2, np.eye(3, dtype=np.float32), np.zeros((1, 5), dtype=np.float32))
+            Rcw, _ = cv2.Rodrigues(rvec)
+            frames.append(dict(tag_ids=ids.tolist(), corners_uv=pix.astype(float).tolist(), Rwc=Rcw.T.tolist(),
+                               twc=(-Rcw.T @ tvec.ravel()).tolist()))
+        out[name] = dict(model=model, intrinsics=k.tolist(), grid=list(grid), points=P.tolist(), pixels=uv.tolist(),
+                         lifted=lift.tolist(), frames=frames)
+    return out
+
+
 if __name__ == "__main__":
+    with open(os.path.join(HERE, "preprocessing.json"), "w") as f:
+        json.dump(preprocessing(), f)
+    with open(os.path.join(HERE, "camera_chain.json"), "w") as f:
+        json.dump(camera_chain(), f)
     with open(os.path.join(HERE, "factor_kat.json"), "w") as f:
         json.dump(factor_kat(), f, indent=1)
     for seed in (1, 2, 3):
