@@ -328,7 +328,7 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)p->grid);
   cfg.blockDim = dim3(clc::kThreads);
-  cfg.dynamicSmemBytes = clc::kDynSmemBytes;
+  cfg.dynamicSmemBytes = clc::dyn_smem_bytes(p->planar);
   cfg.stream = p->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -422,9 +422,11 @@ int finish_create(clc_problem* p) {
         (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, false>,         (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, true>,
         (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, false>,        (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, true>,
         (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, false>, (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, true>};
-    for (const void* fn : variants) {
-      CLC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, clc::kDynSmemBytes));
-      CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, clc::kThreads, clc::kDynSmemBytes));
+    for (int v = 0; v < 6; ++v) {
+      const void* fn = variants[v];
+      const int smem = clc::dyn_smem_bytes((v & 1) != 0);  // odd entries are the planar instantiations
+      CLC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CLC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, clc::kThreads, smem));
       occ_min = std::min(occ_min, occ);
     }
     if (occ_min < 1) return fail(CLC_ERR_CUDA, "the sweep kernel does not fit on this device");

@@ -52,10 +52,12 @@ constexpr int kPlanarChunk = CLC_PLANAR_CHUNK;
 static_assert(kChunk % 64 == 0 && kPlanarChunk % 64 == 0, "stages are made of 64-point groups");
 constexpr int kMaxChunk = kChunk > kPlanarChunk ? kChunk : kPlanarChunk;
 constexpr int kBarsPerWarp = kStages > kPlanarStages ? kStages : kPlanarStages;
-constexpr int kRingDoublesPerWarp =
-    kStages * 3 * kChunk > kPlanarStages * 2 * kPlanarChunk ? kStages * 3 * kChunk : kPlanarStages * 2 * kPlanarChunk;
 constexpr int kTileDoublesPerWarp = 32 * kTileStride;
-constexpr int kDynSmemBytes = kWarps * kRingDoublesPerWarp * 8 + kWarps * kTileDoublesPerWarp * 8 + kWarps * kBarsPerWarp * 8;
+// dynamic shared memory of a kernel family: per-warp ring + per-warp tile + per-warp mbarriers
+__host__ __device__ constexpr int ring_doubles_per_warp(bool planar) { return planar ? kPlanarStages * 2 * kPlanarChunk : kStages * 3 * kChunk; }
+__host__ __device__ constexpr int dyn_smem_bytes(bool planar) {
+  return kWarps * ring_doubles_per_warp(planar) * 8 + kWarps * kTileDoublesPerWarp * 8 + kWarps * kBarsPerWarp * 8;
+}
 
 enum SweepMode { kModeLM = 0, kModeClosedForm = 1 };
 
@@ -287,7 +289,8 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   constexpr int CH = PLANAR ? kPlanarChunk : kChunk;  // points per stage
   constexpr int G = CH / 64;
   constexpr int SST = (PLANAR ? 2 : 3) * CH;  // doubles per stage
-  static_assert(NST * SST <= kRingDoublesPerWarp, "ring too small");
+  constexpr int RING = NST * SST;  // doubles per warp
+  static_assert(RING == ring_doubles_per_warp(PLANAR), "ring size");
   extern __shared__ __align__(128) unsigned char s_dyn[];
   __shared__ double s_acc[kWarps][NOUT];
   __shared__ double s_red[kWarps][32];
@@ -310,9 +313,9 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   int64_t p1 = p0 + pv.per_warp;
   if (p1 > P) p1 = P;
   const int n_chunks = (int)((p1 - p0 + CH - 1) / CH);
-  double* ring = reinterpret_cast<double*>(s_dyn) + warp * kRingDoublesPerWarp;
-  double* tile = reinterpret_cast<double*>(s_dyn) + kWarps * kRingDoublesPerWarp + warp * kTileDoublesPerWarp;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (size_t)kWarps * (kRingDoublesPerWarp + kTileDoublesPerWarp) * 8) + warp * kBarsPerWarp;
+  double* ring = reinterpret_cast<double*>(s_dyn) + warp * RING;
+  double* tile = reinterpret_cast<double*>(s_dyn) + kWarps * RING + warp * kTileDoublesPerWarp;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (size_t)kWarps * (RING + kTileDoublesPerWarp) * 8) + warp * kBarsPerWarp;
 
   auto issue_chunk = [&](int c) {  // lane 0 only
     const int st = c % NST;
