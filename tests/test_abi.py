@@ -150,3 +150,27 @@ def test_compute_entry_points_fail_loudly_without_a_gpu(lib):
     n = C.c_int(-1)
     assert lib.clc_device_count(C.byref(n)) != 0
     assert lib.clc_last_error()
+    # the preparation steps have no host path either
+    from camlasercalibratool_b200 import LineFittingCeres
+    from camlasercalibratool_b200 import formats as fmt
+
+    with pytest.raises(ClcError):
+        LineFittingCeres(np.zeros((5, 3)), np.zeros(2))
+    with pytest.raises(ClcError):
+        fmt.auto_get_line_segments(np.ones((2, 100), dtype=np.float32), -1.0, 0.02, 0.05)
+    with pytest.raises(ClcError):
+        fmt.estimate_board_poses("equi", [(np.array([0], dtype=np.int32), np.zeros((1, 4, 2), dtype=np.float32))])
+
+
+def test_pose_estimation_argument_checks(lib):
+    """clc_estimate_board_poses validates its description before touching the device."""
+    from camlasercalibratool_b200 import ClcError
+    from camlasercalibratool_b200 import formats as fmt
+
+    det = [(np.array([0], dtype=np.int32), np.zeros((1, 4, 2), dtype=np.float32))]
+    with pytest.raises(KeyError):
+        fmt.estimate_board_poses("fisheye", det)
+    for kw in (dict(grid=(0, 6, 0.055, 0.3)), dict(grid=(6, 6, -1.0, 0.3)), dict(intrinsics=[0, 1, 0, 0, 0, 0, 0, 0])):
+        with pytest.raises(ClcError) as exc:
+            fmt.estimate_board_poses("equi", det, **kw)
+        assert "camera" in str(exc.value) or "grid" in str(exc.value)
