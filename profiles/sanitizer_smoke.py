@@ -11,24 +11,38 @@ from camlasercalibratool_b200 import formats as fmt  # noqa: E402
 from oracle import oracle as O  # noqa: E402
 
 x0 = np.array([0, 0, 0, 0, 0, 0, 1.0])
-for edges in (False, True):
-    p = O.generate(60, 150, seed=3, sigma=0.01, exact_m=edges, with_edges=edges)
-    with Problem.from_arrays(p.frame_pose, p.offsets, p.points, p.edge_points) as g:
-        c, H, gr = g.eval(x0)
-        rc, rH, rg = O.evaluate_normal(p, x0)
-        assert abs(c - rc) <= 1e-11 * rc
+os.environ.setdefault("CLC_PLANAR_MIN_POINTS", "0")  # the two-stream kernels also on these small problems
+for planar in ("1", "0"):
+    os.environ["CLC_PLANAR"] = planar
+    for edges in (False, True):
+        p = O.generate(60, 150, seed=3, sigma=0.01, exact_m=edges, with_edges=edges)
+        with Problem.from_arrays(p.frame_pose, p.offsets, p.points, p.edge_points) as g:
+            c, H, gr = g.eval(x0)
+            rc, rH, rg = O.evaluate_normal(p, x0)
+            assert abs(c - rc) <= 1e-11 * rc
+            x, s, tr = g.solve(x0)
+            xo, so, _ = O.solve(p, x0)
+            assert O.pose_error(x, xo)[0] < 1e-8 and s.termination == so.termination
+            g.information(x)
+            g.closed_form()
+            g.line_fit()
+            g.download()
+for planar in ("1", "0"):
+    os.environ["CLC_PLANAR"] = planar
+    with Problem.synthetic(300, 700, seed=2, sigma=0.01, with_edges=True) as g:  # ragged ends of warp ranges, several blocks
+        assert g.planar == (planar == "1")
         x, s, tr = g.solve(x0)
-        xo, so, _ = O.solve(p, x0)
-        assert O.pose_error(x, xo)[0] < 1e-8 and s.termination == so.termination
-        g.information(x)
-        g.closed_form()
-        g.line_fit()
-        g.download()
-with Problem.synthetic(300, 700, seed=2, sigma=0.01, with_edges=True) as g:  # ragged ends of warp ranges, several blocks
-    x, s, tr = g.solve(x0)
-    g.bench_eval(x, 2, flush_l2=False)
+        g.bench_eval(x, 2, flush_l2=False)
+        g.set_planar_mode(1 - int(planar))  # re-partition (and z re-materialised / dropped) on a live problem
+        g.eval(x)
+with Problem.synthetic(40, 64, seed=5, sigma=0.01, camera="equi", pixel_sigma=0.2) as g:  # generator with the camera chain
+    g.solve(x0)
+    g.download_true_poses()
 rng = np.random.default_rng(0)
 ranges = (5 + rng.normal(size=(64, 1081)) * 0.01).astype(np.float32)
 ranges[:, 500:600] = 1.0
 fmt.auto_get_line_segments(ranges, -2.356, 4.712 / 1080, 0.05)
+dets = [(np.arange(36, dtype=np.int32), (rng.uniform(50, 400, size=(36, 4, 2))).astype(np.float32)) for _ in range(70)]
+dets.append((np.zeros(0, dtype=np.int32), np.zeros((0, 4, 2), dtype=np.float32)))
+fmt.estimate_board_poses("radtan", dets)
 print("sanitizer smoke ok")
