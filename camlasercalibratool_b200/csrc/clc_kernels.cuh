@@ -271,8 +271,8 @@ __device__ __forceinline__ void renormalise(Moments& a) {
 //
 // Work decomposition: the P points are cut into equal contiguous ranges (a multiple of 128 points), one per warp of
 // a grid that fills the machine exactly once (persistent: SM count x resident blocks).  Every warp owns a private
-// 3-stage ring in shared memory that the TMA engine fills with 1 KiB bulk copies (cp.async.bulk, one per coordinate
-// array and stage; completion on an mbarrier), so ~9 KiB per warp / ~144 KiB per SM are in flight regardless of
+// 2-stage ring in shared memory that the TMA engine fills with 1 KiB bulk copies (cp.async.bulk, one per coordinate
+// array and stage; completion on an mbarrier), so ~6 KiB per warp / ~96 KiB per SM are in flight regardless of
 // register pressure and independent of the frame bookkeeping.  The warp consumes a stage with conflict-free 128-bit
 // shared loads (4 points per lane), walks the frame pieces that overlap the stage, and keeps 10 weighted moments
 // plus the running cost product per lane in registers.  When a frame ends, the lanes' moments are summed by warp
@@ -512,7 +512,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
         if (hi == f_end) park_piece();
       }
       // every lane has consumed its registers' worth of the stage (data dependence), so the slot can be handed
-      // back to the TMA engine: two more stages stay in flight meanwhile
+      // back to the TMA engine: the other stage stays in flight meanwhile
       __syncwarp();
       if (lane == 0 && ch + NST < n_chunks) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
