@@ -208,3 +208,21 @@ def test_save_plane_points_files(tmp_path, oracle):
     assert np.array_equal(roi[:, 0], np.repeat(np.arange(12), np.diff(p.offsets)))
     for tok in (tmp_path / "planar.txt").read_text().split():
         assert "%.3g" % float(tok) == tok  # std::setprecision(3), default float format
+
+
+def test_offline_driver_refuses_too_little_data():
+    """reference main/calibr_offline.cpp:55-59 (fewer than 10 tag poses) and :158-163 (fewer than 5 matched observations):
+    both exits are taken before any numeric work, so they are testable without a GPU."""
+    from camlasercalibratool_b200.formats import CamPose, calibrate_offline, observations_from_segments
+
+    poses = [CamPose(0.1 * i, np.array([0, 0, 0, 1.0]), np.array([0.0, 0.0, 1.0 + 0.3 * i])) for i in range(9)]
+    Tlc, why = calibrate_offline(poses, [])
+    assert Tlc is None and why == "apriltag pose less than 10."
+    poses.append(CamPose(0.9, np.array([0, 0, 0, 1.0]), np.array([0.0, 0.0, 4.0])))
+    # scans whose time stamps are more than 20 ms away from every pose are not matched (:116)
+    scans = [(0.1 * i + 0.05, np.array([[1.0, 0.1 * i, 0.0], [1.0, 0.1 * i + 0.2, 0.0]])) for i in range(10)]
+    assert observations_from_segments(poses, scans) == []
+    Tlc, why = calibrate_offline(poses, scans)
+    assert Tlc is None and why == "Valid Calibra Data Less"
+    # empty segments are skipped, too
+    assert observations_from_segments(poses, [(0.1, np.zeros((0, 3)))]) == []
