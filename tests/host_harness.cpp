@@ -46,6 +46,12 @@ void harness_expand_closed(const double* plane, const double* S10, double* out54
 void harness_frame_plane(const double* fp, double* plane) { clc::frame_plane(fp, plane); }
 void harness_edge_planes(const double* fp, double* p1, double* p2) { clc::edge_planes(fp, p1, p2); }
 void harness_pose_plus(const double* x, const double* d, double* xp) { clc::pose_plus(x, d, xp); }
+void harness_quat_to_rot(const double* q, double* R) { clc::quat_to_rot(q, R); }
+void harness_rot_to_quat(const double* R, double* q) { clc::rot_to_quat(R, q); }
+int harness_chol6_solve(const double* A, const double* b, double* y) { return clc::chol6_solve(A, b, y) ? 1 : 0; }
+int harness_solve_linear(double* A, double* b, int n) { return clc::solve_linear(A, b, n) ? 1 : 0; }
+double harness_equi_r(const double* k, double th) { return clc::equi_r(k, th); }
+double harness_equi_theta_from_r(const double* k, double rn) { return clc::equi_theta_from_r(k, rn); }
 void harness_philox(uint64_t seed, uint64_t lo, uint64_t hi, uint32_t* out) { clc::philox4x32(seed, lo, hi, out); }
 void harness_gen_frame_pose(uint64_t seed, int64_t frame, int with_edges, double* fp) {
   clc::gen_frame_pose(seed, frame, with_edges != 0, fp);
