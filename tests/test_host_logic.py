@@ -206,3 +206,40 @@ def test_generator_twin(harness, oracle):
                 ep = np.empty(6)
                 assert harness.L.harness_gen_edge_points(harness.dp(fp), harness.dp(ep)) == 1
                 np.testing.assert_allclose(ep, p.edge_points[f], rtol=0, atol=1e-13)
+
+
+def test_state_machine_soak_on_random_problems(harness, oracle):
+    """80 random problems (sizes, noise, loss on/off, edge residuals, starts from exact to far off): the device LM code
+    (Cholesky on the normal equations) takes the same accept/reject decisions and stops for the same reason as the
+    Ceres-shaped oracle (Householder QR on the materialised Jacobian).  A 400-problem run of the same loop was clean."""
+    rng = np.random.default_rng(12345)
+    seen = set()
+    for _ in range(80):
+        n_frames, beams = int(rng.integers(5, 60)), int(rng.integers(20, 200))
+        sigma = float(rng.choice([0.0, 0.005, 0.01, 0.03]))
+        edges, loss = bool(rng.random() < 0.3), bool(rng.random() < 0.8)
+        p = oracle.generate(n_frames, beams, seed=int(rng.integers(1, 10**6)), sigma=sigma, with_edges=edges, exact_m=edges,
+                            use_loss=loss)
+        if p.n_points == 0:
+            continue
+        scale = float(rng.choice([0.0, 0.05, 0.5, 2.0]))
+        x0 = X0
+        if scale > 0:
+            if rng.random() < 0.7:
+                x0 = oracle.pose_plus(oracle.ground_truth()[1], rng.normal(size=6) * scale)
+            else:
+                q = rng.normal(size=4)
+                x0 = np.concatenate([rng.normal(size=3) * scale, q / np.linalg.norm(q)])
+
+        def sums(pose):
+            c, H, g = oracle.evaluate_normal(p, pose)
+            return pack_sums(c, H, g)
+
+        x, done, trace, sweeps = harness.lm_run(sums, x0)
+        xo, so, tro = oracle.solve(p, x0)
+        assert done == so.termination and len(trace) == so.num_iterations
+        assert all((a.step_is_valid, a.step_is_successful) == (b.step_is_valid, b.step_is_successful) for a, b in zip(trace, tro))
+        ang, dt = oracle.pose_error(x, xo)
+        assert ang < 1e-6 and dt < 1e-6
+        seen.add(so.termination)
+    assert len(seen) >= 3  # function / parameter / gradient tolerance (and sometimes the iteration limit) all occur
