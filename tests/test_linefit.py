@@ -105,3 +105,51 @@ def test_batched_line_fit_matches_oracle(oracle):
     line = np.zeros(2)
     LineFittingCeres(scans[7], line)
     np.testing.assert_allclose(line, oracle.line_fit(scans[7], (0, 0))[0], atol=1e-9)
+
+
+def test_two_parameter_state_machine_soak(harness, oracle):
+    """300 random scans incl. degenerate ones (1-3 points, all points identical, gross outliers, 1000x scale, odd starts,
+    0 / 3 / 50 iteration limits): the device state machine ends for the same reason and at the same line as the oracle.
+    (Scans through the sensor origin, where m.p + 1 = 0 has no solution and J is rank deficient, agree only to ~1e-7 --
+    normal equations vs QR on a singular problem -- and are left out; a board cannot pass through the laser.)"""
+    L = harness.L
+    dp = C.POINTER(C.c_double)
+    L.harness_lm2_size.restype = C.c_int
+    L.harness_lm2_init.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    L.harness_lm2_update.argtypes = [C.c_void_p, dp, C.c_int]
+    L.harness_lm2_done.argtypes = [C.c_void_p]
+    L.harness_lm2_get.argtypes = [C.c_void_p, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rng = np.random.default_rng(99)
+    seen = set()
+    for _ in range(300):
+        n = int(rng.choice([1, 2, 3, 5, 20, 100, 400]))
+        kind = int(rng.integers(0, 4))
+        ang, d = rng.uniform(0, 2 * np.pi), rng.uniform(0.3, 5.0)
+        t = rng.uniform(-1, 1, size=n) * rng.uniform(0.05, 2.0)
+        nrm = np.array([np.cos(ang), np.sin(ang)])
+        pts2 = d * nrm + t[:, None] * np.array([-nrm[1], nrm[0]]) + rng.normal(size=(n, 2)) * rng.choice([0.0, 0.002, 0.02])
+        if kind == 1:
+            pts2[rng.random(n) < 0.2] += rng.normal(size=2)
+        elif kind == 2:
+            pts2[:] = pts2[0]
+        elif kind == 3:
+            pts2 *= 1e3
+        pts = np.c_[pts2, np.zeros(n)]
+        start = [(0.0, 0.0), tuple(rng.normal(size=2) * 3), tuple(-nrm / d)][int(rng.integers(0, 3))]
+        max_iter = int(rng.choice([10, 10, 3, 0, 50]))
+        st = C.create_string_buffer(L.harness_lm2_size())
+        L.harness_lm2_init(st, start[0], start[1])
+        cand, x = np.empty(2), np.empty(2)
+        it, sw = C.c_int(), C.c_int()
+        for _guard in range(200):
+            if L.harness_lm2_done(st):
+                break
+            L.harness_lm2_get(st, cand.ctypes.data_as(dp), x.ctypes.data_as(dp), C.byref(it), C.byref(sw))
+            sums = line_sums(pts, cand.copy())
+            L.harness_lm2_update(st, sums.ctypes.data_as(dp), max_iter)
+        L.harness_lm2_get(st, cand.ctypes.data_as(dp), x.ctypes.data_as(dp), C.byref(it), C.byref(sw))
+        lo, so, _ = oracle.line_fit(pts, start, max_num_iterations=max_iter)
+        assert L.harness_lm2_done(st) == so.termination
+        np.testing.assert_allclose(x, lo, rtol=0, atol=1e-9 * max(1.0, np.abs(lo).max()))
+        seen.add(so.termination)
+    assert len(seen) >= 3
