@@ -226,3 +226,42 @@ def test_offline_driver_refuses_too_little_data():
     assert Tlc is None and why == "Valid Calibra Data Less"
     # empty segments are skipped, too
     assert observations_from_segments(poses, [(0.1, np.zeros((0, 3)))]) == []
+
+
+def test_scan_segmentation_soak_with_pathological_scans(harness, oracle, oracle_np):
+    """600 random scans -- 0 to 2000 beams, boards of any width and distance, NaN / inf / zero / negative / huge ranges,
+    constant scans -- through the C oracle, the literal numpy twin and the host build of the device code: always the same
+    answer (a 3000-scan run of the same loop was clean)."""
+    import ctypes as C
+
+    L = harness.L
+    L.harness_auto_get_line_pts.argtypes = [C.POINTER(C.c_float), C.c_int64, C.c_double, C.c_double, C.c_double,
+                                            C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rng = np.random.default_rng(5)
+    found = 0
+    for _ in range(600):
+        n = int(rng.choice([0, 1, 5, 40, 99, 100, 101, 360, 720, 1081, 2000]))
+        a0, inc = rng.uniform(-3.2, 0), rng.uniform(0.001, 0.02)
+        ang = a0 + np.arange(n) * inc
+        r = (rng.uniform(1, 8) + np.sin(ang * rng.uniform(1, 5) + rng.uniform(0, 6)) * rng.uniform(0, 2)
+             + rng.normal(size=n) * 0.01).astype(np.float32)
+        kind = int(rng.integers(0, 8))
+        if n > 10 and kind < 5:
+            c, w, d = rng.uniform(ang[0], ang[-1]), rng.uniform(0.02, 0.6), rng.uniform(0.2, 3.0)
+            m = np.abs(ang - c) < w
+            r[m] = (d / np.cos(np.clip(ang[m] - c, -1.4, 1.4)) + rng.normal(size=int(m.sum())) * rng.choice([0, 0.003, 0.02])).astype(np.float32)
+        if kind == 5 and n:
+            r[rng.random(n) < 0.3] = np.nan
+        if kind == 6 and n:
+            r[rng.random(n) < 0.3] = rng.choice([0.0, -1.0, np.inf, 1e9])
+        if kind == 7 and n:
+            r[:] = rng.choice([0.5, 2.0, 40.0])
+        rmin = float(rng.choice([0.05, 0.0, 0.5]))
+        ref = oracle.auto_get_line_pts(oracle.scan_to_points(r, a0, inc, rmin)) if n else None
+        twin = oracle_np.auto_get_line_pts(oracle_np.scan_to_points(r, a0, inc, rmin)) if n else None
+        s, e = C.c_int(), C.c_int()
+        L.harness_auto_get_line_pts(r.ctypes.data_as(C.POINTER(C.c_float)), n, a0, inc, rmin, C.byref(s), C.byref(e))
+        got = None if s.value < 0 else (s.value, e.value)
+        assert ref == twin == got
+        found += ref is not None
+    assert found > 10
