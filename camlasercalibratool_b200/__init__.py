@@ -11,18 +11,21 @@ from .api import (  # noqa: F401
     LineFittingCeres,
     ClcError,
     Comm,
+    Group,
     Oberserve,
     Problem,
     T_to_pose7,
     comm_unique_id,
+    debug_pack,
     default_options,
     launch_count,
     marshal,
     pose7_to_T,
     shard_range,
+    upload_stats,
 )
 
 __all__ = [
-    "CamLaserCalClosedSolution", "CamLaserCalibration", "LineFittingCeres", "ClcError", "Comm", "Oberserve", "Problem", "T_to_pose7",
-    "comm_unique_id", "default_options", "launch_count", "marshal", "pose7_to_T", "shard_range",
+    "CamLaserCalClosedSolution", "CamLaserCalibration", "LineFittingCeres", "ClcError", "Comm", "Group", "Oberserve", "Problem", "T_to_pose7",
+    "comm_unique_id", "default_options", "launch_count", "marshal", "pose7_to_T", "shard_range", "debug_pack", "upload_stats",
 ]

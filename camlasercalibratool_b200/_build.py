@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libclc_b200.so")
 SOURCES = ["clc_api.cu"]
-HEADERS = ["clc_kernels.cuh", "clc_math.cuh", "clc_lm.cuh", "clc_expand.cuh", "clc_linefit.cuh", "clc_camera.cuh"]
+HEADERS = ["clc_kernels.cuh", "clc_math.cuh", "clc_lm.cuh", "clc_expand.cuh", "clc_linefit.cuh", "clc_camera.cuh", "clc_upload.inl"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -51,5 +51,44 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return out
 
 
+# ---- the C++ side: the drop-in translation unit + the end-to-end bench driver (g++, no CUDA headers needed) -----------
+REPO = os.path.dirname(PKG_DIR)
+DROPIN_SRC = os.path.join(PKG_DIR, "host", "LaseCamCalB200.cpp")
+BENCH_SRC = os.path.join(PKG_DIR, "host", "dropin_bench.cpp")
+BENCH_EXE = os.path.join(PKG_DIR, "host", "clc_dropin_bench")
+REFERENCE_INCLUDE = "/root/reference/include"
+
+
+def interface_include_dirs():
+    """Include path of the reference interface: the reference's own include/LaseCamCalCeres.h when the tree is present
+    (build container), else the test stand-in; Eigen itself is not in this image, so its few types come from tests/stubs."""
+    dirs = []
+    if os.path.exists(os.path.join(REFERENCE_INCLUDE, "LaseCamCalCeres.h")):
+        dirs.append(REFERENCE_INCLUDE)
+    dirs.append(os.path.join(REPO, "tests", "stubs"))
+    dirs.append(os.path.join(REPO, "include"))
+    return dirs
+
+
+def cxx_command(sources, out, extra=()):
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++11", "-Wall"]
+    for d in interface_include_dirs():
+        cmd += ["-I", d]
+    cmd += list(sources) + ["-L", PKG_DIR, "-lclc_b200", "-Wl,-rpath," + PKG_DIR, "-Wl,-rpath,$ORIGIN/..", "-pthread", *extra, "-o", out]
+    return cmd
+
+
+def build_dropin_bench(force: bool = False) -> str:
+    deps = [DROPIN_SRC, BENCH_SRC, os.path.join(REPO, "include", "clc_b200.h"), LIB_PATH]
+    if not force and os.path.exists(BENCH_EXE) and all(os.path.getmtime(d) <= os.path.getmtime(BENCH_EXE) for d in deps if os.path.exists(d)):
+        return BENCH_EXE
+    res = subprocess.run(cxx_command([BENCH_SRC, DROPIN_SRC], BENCH_EXE), capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stdout + res.stderr)
+    return BENCH_EXE
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_dropin_bench(force=True))

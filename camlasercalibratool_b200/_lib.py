@@ -30,6 +30,19 @@ class ProblemDesc(C.Structure):
     ]
 
 
+class GatherDesc(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int64),
+        ("frame_pose", c_double_p),
+        ("frame_points", C.POINTER(c_double_p)),
+        ("frame_counts", c_int64_p),
+        ("edge_points", c_double_p),
+        ("use_loss", C.c_int),
+        ("cauchy_a", C.c_double),
+        ("device", C.c_int),
+    ]
+
+
 class SyntheticDesc(C.Structure):
     _fields_ = [
         ("n_frames_total", C.c_int64),
@@ -130,7 +143,19 @@ SIGNATURES = {
     "clc_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "clc_lm_default_options": (None, [C.POINTER(LmOptions)]),
     "clc_problem_create": (C.c_int, [C.POINTER(_P), C.POINTER(ProblemDesc)]),
+    "clc_problem_create_gather": (C.c_int, [C.POINTER(_P), C.POINTER(GatherDesc)]),
     "clc_problem_create_synthetic": (C.c_int, [C.POINTER(_P), C.POINTER(SyntheticDesc)]),
+    "clc_group_create_gather": (C.c_int, [C.POINTER(_P), C.POINTER(GatherDesc), C.POINTER(C.c_int), C.c_int]),
+    "clc_group_create_synthetic": (C.c_int, [C.POINTER(_P), C.POINTER(SyntheticDesc), C.POINTER(C.c_int), C.c_int]),
+    "clc_group_destroy": (C.c_int, [_P]),
+    "clc_group_size": (C.c_int, [_P, C.POINTER(C.c_int), c_int64_p, c_int64_p]),
+    "clc_group_problem": (C.c_int, [_P, C.c_int, C.POINTER(_P)]),
+    "clc_group_eval": (C.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "clc_group_solve_lm": (C.c_int, [_P, c_double_p, C.POINTER(LmOptions), C.POINTER(LmSummary), C.POINTER(LmIteration), C.c_int]),
+    "clc_group_information": (C.c_int, [_P, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "clc_group_closed_form": (C.c_int, [_P, c_double_p, C.POINTER(C.c_int), c_double_p, c_double_p]),
+    "clc_default_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]),
+    "clc_upload_last_stats": (C.c_int, [c_double_p, c_double_p, c_int64_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "clc_problem_destroy": (C.c_int, [_P]),
     "clc_problem_sizes": (C.c_int, [_P, c_int64_p, c_int64_p, C.POINTER(C.c_int)]),
     "clc_problem_download": (C.c_int, [_P, c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p]),
@@ -159,6 +184,10 @@ SIGNATURES = {
     "clc_problem_algorithmic_bytes": (C.c_int, [_P, c_int64_p]),
     "clc_problem_streamed_bytes": (C.c_int, [_P, c_int64_p]),
     "clc_problem_set_planar_mode": (C.c_int, [_P, C.c_int]),
+    "clc_debug_pack": (C.c_int, [C.c_int64, C.POINTER(c_double_p), c_int64_p, C.c_int64, C.c_int64, C.c_int, c_double_p,
+                                 C.POINTER(C.c_int)]),
+    "clc_bench_h2d": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "clc_solve_readback_bytes": (C.c_int64, []),
     "clc_host_alloc": (C.c_int, [C.POINTER(_P), C.c_int64]),
     "clc_host_free": (C.c_int, [_P]),
     "clc_launch_count": (C.c_int64, []),

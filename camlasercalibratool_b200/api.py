@@ -14,7 +14,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _lib
-from ._lib import ClcError, LmIteration, LmOptions, LmSummary, ProblemDesc, SyntheticDesc, TERMINATION
+from ._lib import ClcError, GatherDesc, LmIteration, LmOptions, LmSummary, ProblemDesc, SyntheticDesc, TERMINATION
 
 
 def _dp(a):
@@ -74,6 +74,48 @@ CAMERA_DEFAULTS = {
 }
 
 
+class _Gather:
+    """Keeps the arrays of a clc_gather_desc alive: one separate [n_i, 3] array per frame, as std::vector<Oberserve> holds
+    them (reference include/LaseCamCalCeres.h:22-23)."""
+
+    def __init__(self, frame_pose, frames, edge_points=None, use_loss=True, cauchy_a=0.05, device=-1):
+        self.frame_pose = np.ascontiguousarray(frame_pose, dtype=np.float64).reshape(-1, 7)
+        self.frames = [np.ascontiguousarray(f, dtype=np.float64).reshape(-1, 3) for f in frames]
+        n = self.frame_pose.shape[0]
+        if len(self.frames) != n:
+            raise ValueError("one point array per frame is needed")
+        self.counts = np.array([f.shape[0] for f in self.frames], dtype=np.int64)
+        self.ptrs = (_lib.c_double_p * max(n, 1))(*[_dp(f) for f in self.frames])
+        self.edge = None
+        if edge_points is not None:
+            self.edge = np.ascontiguousarray(edge_points, dtype=np.float64).reshape(-1, 6)
+            if self.edge.shape[0] != n:
+                raise ValueError("edge_points must be [n_frames, 6]")
+        d = GatherDesc()
+        d.n_frames = n
+        d.frame_pose, d.frame_points, d.frame_counts, d.edge_points = _dp(self.frame_pose), self.ptrs, _ip(self.counts), _dp(self.edge)
+        d.use_loss, d.cauchy_a, d.device = int(bool(use_loss)), float(cauchy_a), int(device)
+        self.desc = d
+
+
+def _synthetic_desc(n_frames_total, beams, seed, sigma, with_edges, frame_begin, frame_end, use_loss, cauchy_a, device, camera,
+                    pixel_sigma, intrinsics, image_size, grid):
+    d = SyntheticDesc()
+    d.n_frames_total = int(n_frames_total)
+    d.frame_begin = int(frame_begin)
+    d.frame_end = int(n_frames_total if frame_end is None else frame_end)
+    d.beams, d.seed, d.sigma = int(beams), int(seed), float(sigma)
+    d.with_edges, d.use_loss, d.cauchy_a, d.device = int(bool(with_edges)), int(bool(use_loss)), float(cauchy_a), int(device)
+    d.camera_model = {None: 0, "none": 0, "radtan": 1, "pinhole": 1, "equi": 2}[camera]
+    if d.camera_model:
+        k = CAMERA_DEFAULTS["radtan" if d.camera_model == 1 else "equi"] if intrinsics is None else intrinsics
+        d.camera_intrinsics = (C.c_double * 8)(*[float(v) for v in k])
+        d.pixel_sigma = float(pixel_sigma)
+        d.image_width, d.image_height = int(image_size[0]), int(image_size[1])
+        d.grid_rows, d.grid_cols, d.tag_size, d.tag_spacing = int(grid[0]), int(grid[1]), float(grid[2]), float(grid[3])
+    return d
+
+
 def default_options(**kw) -> LmOptions:
     o = LmOptions()
     _lib.load().clc_lm_default_options(C.byref(o))
@@ -112,6 +154,14 @@ class Problem:
         return cls(h)
 
     @classmethod
+    def from_frames(cls, frame_pose, frames, edge_points=None, use_loss=True, cauchy_a=0.05, device=-1):
+        """One separate [n_i, 3] array per frame (clc_problem_create_gather): the library gathers them itself."""
+        g = _Gather(frame_pose, frames, edge_points, use_loss, cauchy_a, device)
+        h = C.c_void_p()
+        _lib.check(_lib.load().clc_problem_create_gather(C.byref(h), C.byref(g.desc)), "clc_problem_create_gather")
+        return cls(h)
+
+    @classmethod
     def from_observations(cls, obs, use_linefitting_data=True, use_boundary_constraint=False, **kw):
         fp, off, pts, edge = marshal(obs, use_linefitting_data, use_boundary_constraint)
         return cls.from_arrays(fp, off, pts, edge, **kw)
@@ -124,19 +174,8 @@ class Problem:
         (Kannala-Brandt, mu mv u0 v0 k2 k3 k4 k5): the poses handed to the solver are then estimated from noisy corner
         pixels by the reference's undistort + PnP chain.  Default intrinsics: the reference's config/*.yaml."""
         L = _lib.load()
-        d = SyntheticDesc()
-        d.n_frames_total = int(n_frames_total)
-        d.frame_begin = int(frame_begin)
-        d.frame_end = int(n_frames_total if frame_end is None else frame_end)
-        d.beams, d.seed, d.sigma = int(beams), int(seed), float(sigma)
-        d.with_edges, d.use_loss, d.cauchy_a, d.device = int(bool(with_edges)), int(bool(use_loss)), float(cauchy_a), int(device)
-        d.camera_model = {None: 0, "none": 0, "radtan": 1, "pinhole": 1, "equi": 2}[camera]
-        if d.camera_model:
-            k = CAMERA_DEFAULTS["radtan" if d.camera_model == 1 else "equi"] if intrinsics is None else intrinsics
-            d.camera_intrinsics = (C.c_double * 8)(*[float(v) for v in k])
-            d.pixel_sigma = float(pixel_sigma)
-            d.image_width, d.image_height = int(image_size[0]), int(image_size[1])
-            d.grid_rows, d.grid_cols, d.tag_size, d.tag_spacing = int(grid[0]), int(grid[1]), float(grid[2]), float(grid[3])
+        d = _synthetic_desc(n_frames_total, beams, seed, sigma, with_edges, frame_begin, frame_end, use_loss, cauchy_a, device,
+                            camera, pixel_sigma, intrinsics, image_size, grid)
         h = C.c_void_p()
         _lib.check(L.clc_problem_create_synthetic(C.byref(h), C.byref(d)), "clc_problem_create_synthetic")
         return cls(h)
@@ -251,6 +290,122 @@ class Problem:
         ms = (C.c_float * n)()
         _lib.check(self._L.clc_bench_eval(self._h, _dp(pose7), int(n), int(bool(flush_l2)), ms), "clc_bench_eval")
         return np.array(ms[:], dtype=np.float64)
+
+
+class Group:
+    """G devices of THIS process solving one problem (clc_group_*): frames sharded by point count, the 28 sums exchanged
+    over NVLink inside the sweep kernel, one host thread.  A group of one device is a plain problem."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self._L = _lib.load()
+
+    @staticmethod
+    def _devices(devices):
+        devs = [int(d) for d in devices]
+        return (C.c_int * len(devs))(*devs), len(devs)
+
+    @classmethod
+    def from_frames(cls, frame_pose, frames, edge_points=None, devices=(-1,), use_loss=True, cauchy_a=0.05):
+        g = _Gather(frame_pose, frames, edge_points, use_loss, cauchy_a)
+        arr, n = cls._devices(devices)
+        h = C.c_void_p()
+        _lib.check(_lib.load().clc_group_create_gather(C.byref(h), C.byref(g.desc), arr, n), "clc_group_create_gather")
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, frame_pose, offsets, points, edge_points=None, devices=(-1,), **kw):
+        points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        offsets = np.asarray(offsets, dtype=np.int64)
+        frames = [points[offsets[f]:offsets[f + 1]] for f in range(len(offsets) - 1)]
+        return cls.from_frames(frame_pose, frames, edge_points, devices, **kw)
+
+    @classmethod
+    def synthetic(cls, n_frames, beams, seed=1, sigma=0.0, with_edges=False, devices=(-1,), use_loss=True, cauchy_a=0.05,
+                  n_frames_total=None, frame_begin=0, camera=None, pixel_sigma=0.0, intrinsics=None, image_size=(752, 480),
+                  grid=(6, 6, 0.055, 0.3)):
+        total = int(n_frames_total if n_frames_total is not None else frame_begin + n_frames)
+        d = _synthetic_desc(total, beams, seed, sigma, with_edges, frame_begin, frame_begin + n_frames, use_loss, cauchy_a, -1,
+                            camera, pixel_sigma, intrinsics, image_size, grid)
+        arr, n = cls._devices(devices)
+        h = C.c_void_p()
+        _lib.check(_lib.load().clc_group_create_synthetic(C.byref(h), C.byref(d), arr, n), "clc_group_create_synthetic")
+        return cls(h)
+
+    def close(self):
+        if self._h is not None:
+            self._L.clc_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sizes(self):
+        n, nf, npts = C.c_int(), C.c_int64(), C.c_int64()
+        _lib.check(self._L.clc_group_size(self._h, C.byref(n), C.byref(nf), C.byref(npts)), "clc_group_size")
+        return n.value, nf.value, npts.value
+
+    def problem(self, index):
+        """Borrowed view of shard `index` (do not close it)."""
+        h = C.c_void_p()
+        _lib.check(self._L.clc_group_problem(self._h, int(index), C.byref(h)), "clc_group_problem")
+        p = Problem(h)
+        p.close = lambda: None  # owned by the group
+        return p
+
+    def eval(self, pose7):
+        pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
+        H, g, cost = np.empty((6, 6)), np.empty(6), C.c_double()
+        _lib.check(self._L.clc_group_eval(self._h, _dp(pose7), _dp(H), _dp(g), C.byref(cost)), "clc_group_eval")
+        return cost.value, H, g
+
+    def solve(self, pose7, options: LmOptions | None = None, trace_cap=256):
+        x = np.ascontiguousarray(pose7, dtype=np.float64).copy()
+        o = options if options is not None else default_options()
+        s = LmSummary()
+        tr = (LmIteration * trace_cap)()
+        _lib.check(self._L.clc_group_solve_lm(self._h, _dp(x), C.byref(o), C.byref(s), tr, trace_cap), "clc_group_solve_lm")
+        return x, s, [tr[i] for i in range(min(s.num_iterations, trace_cap))]
+
+    def information(self, pose7):
+        pose7 = np.ascontiguousarray(pose7, dtype=np.float64)
+        H, b, sv, chi = np.empty((6, 6)), np.empty(6), np.empty(6), C.c_double()
+        self.last_V = np.empty((6, 6))
+        _lib.check(self._L.clc_group_information(self._h, _dp(pose7), _dp(H), _dp(b), C.byref(chi), _dp(sv), _dp(self.last_V)),
+                   "clc_group_information")
+        return H, b, chi.value, sv
+
+    def closed_form(self):
+        T, AtA, Atb, un = np.empty(16), np.empty((9, 9)), np.empty(9), C.c_int()
+        _lib.check(self._L.clc_group_closed_form(self._h, _dp(T), C.byref(un), _dp(AtA), _dp(Atb)), "clc_group_closed_form")
+        return T.reshape(4, 4), bool(un.value), AtA, Atb
+
+
+def upload_stats():
+    """Statistics of this process's most recent host -> HBM upload (clc_upload_last_stats)."""
+    t, w, b = C.c_double(), C.c_double(), C.c_int64()
+    ch, th, di = C.c_int(), C.c_int(), C.c_int()
+    _lib.load().clc_upload_last_stats(C.byref(t), C.byref(w), C.byref(b), C.byref(ch), C.byref(th), C.byref(di))
+    return dict(total_ms=t.value, pack_wait_ms=w.value, bytes_h2d=b.value, chunks=ch.value, pack_threads=th.value, direct=bool(di.value))
+
+
+def debug_pack(frames, a, b, xy):
+    """What the pack threads write for the local point range [a, b) (test hook; no CUDA)."""
+    g = _Gather(np.zeros((len(frames), 7)), frames)
+    out = np.empty((b - a) * (2 if xy else 3))
+    nonplanar = C.c_int(-1)
+    _lib.check(_lib.load().clc_debug_pack(len(frames), g.ptrs, _ip(g.counts), int(a), int(b), int(bool(xy)), _dp(out),
+                                          C.byref(nonplanar)), "clc_debug_pack")
+    return out.reshape(-1, 2 if xy else 3), nonplanar.value
 
 
 class Comm:

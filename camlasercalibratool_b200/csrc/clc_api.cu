@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -188,6 +189,7 @@ int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 struct PinnedBlock {
   clc::LmState lm;
   double sums[clc::kMaxOut];
+  double pose[8];
   int done;
   int nonplanar;
 };
@@ -222,6 +224,7 @@ struct clc_comm {
   void* p2p_block = nullptr;
   void* peer_block[clc::kMaxRanks] = {};
   bool p2p_ready = false;
+  bool local = false;  // in-process group: peer_block[] are plain peer-access pointers (no IPC handles, no NCCL communicator)
   size_t mailbox_bytes() const { return sizeof(unsigned long long) * 2 * 2 * (size_t)nranks * clc::kMailboxSlot; }
   size_t block_bytes() const { return mailbox_bytes() + sizeof(unsigned long long); }  // + exchange counter
 };
@@ -269,6 +272,7 @@ struct clc_problem {
   // planar data (every z exactly 0: a 2-D laser): the z stream is dropped and the two-stream kernels run
   int* d_nonplanar = nullptr;  // raised by the upload kernel when a z != 0 was seen
   bool z_all_zero = false;     // property of the data
+  bool host_planarity_known = false;  // the host packers checked every z (clc_upload.inl): no device-side verdict to fetch
   bool planar = false;         // the two-stream kernels are in use (z_all_zero && planar_mode != 0 && large enough)
   int planar_mode = 1;         // 1 = automatic (default), 0 = always the general three-stream kernels
   int64_t planar_min_points = 0;
@@ -360,10 +364,10 @@ int allreduce_sums(clc_problem* p, int count) {
 
 // a peer that never answered the in-kernel exchange (5 s time-out) is an error, not a hang
 int check_p2p_error(clc_problem* p) {
-  if (p->nranks <= 1 || p->allreduce_mode != 1) return CLC_OK;
   int err = 0;
   CLC_CUDA(cudaMemcpyAsync(&err, p->p2p_error, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
   CLC_CUDA(cudaStreamSynchronize(p->stream));
+  if (err == 2) return fail(CLC_ERR_CUDA, "sweep kernel: the persistent grid was not co-resident (ticket wait timed out)");
   if (err) return fail(CLC_ERR_NCCL, "peer exchange timed out: a rank did not reach the collective");
   return CLC_OK;
 }
@@ -453,10 +457,14 @@ int finish_create(clc_problem* p) {
   p->h_sums = p->pinned->sums;
   p->h_done = &p->pinned->done;
   p->h_lm = &p->pinned->lm;
-  p->pinned->nonplanar = 1;
-  CLC_CUDA(cudaMemcpyAsync(&p->pinned->nonplanar, p->d_nonplanar, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-  CLC_CUDA(cudaStreamSynchronize(p->stream));
-  p->z_all_zero = p->pinned->nonplanar == 0;
+  if (p->host_planarity_known) {
+    CLC_CUDA(cudaStreamSynchronize(p->stream));
+  } else {
+    p->pinned->nonplanar = 1;
+    CLC_CUDA(cudaMemcpyAsync(&p->pinned->nonplanar, p->d_nonplanar, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CLC_CUDA(cudaStreamSynchronize(p->stream));
+    p->z_all_zero = p->pinned->nonplanar == 0;
+  }
   if (const char* env = std::getenv("CLC_PLANAR")) p->planar_mode = std::atoi(env) != 0 ? 1 : 0;
   // The planar kernels stream 256-point stages; they pay off once every warp of the full grid has at least one such stage.
   // Smaller problems (the reference's own 50 x 180) are latency-bound and keep the 128-point stages of the general kernels.
@@ -540,6 +548,13 @@ int materialise_z(clc_problem* p) {
 
 }  // namespace
 
+struct clc_group;
+extern "C" int clc_problem_destroy(clc_problem* p);
+extern "C" int clc_group_create_gather(clc_group** out, const clc_gather_desc* desc, const int* devices, int n_devices);
+static clc_problem* group_release_single(clc_group* g);
+
+#include "clc_upload.inl"
+
 extern "C" {
 
 const char* clc_last_error(void) { return g_last_error.c_str(); }
@@ -605,37 +620,43 @@ int clc_problem_destroy(clc_problem* p) {
   return CLC_OK;
 }
 
-int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
-  if (!out || !d) return fail(CLC_ERR_INVALID, "NULL argument");
-  *out = nullptr;
-  if (d->n_frames < 0 || (d->n_frames > 0 && (!d->frame_pose || !d->offsets)))
-    return fail(CLC_ERR_INVALID, "frame_pose/offsets missing");
-  if (!(d->cauchy_a > 0.0)) return fail(CLC_ERR_INVALID, "cauchy_a must be positive");
-  const int64_t N = d->n_frames;
-  const int64_t P = N > 0 ? d->offsets[N] : 0;
-  if (N > 0 && d->offsets[0] != 0) return fail(CLC_ERR_INVALID, "offsets[0] must be 0");
-  for (int64_t f = 0; f < N; ++f)
-    if (d->offsets[f + 1] < d->offsets[f]) return fail(CLC_ERR_INVALID, "offsets must be non-decreasing");
-  if (P > 0 && !d->points) return fail(CLC_ERR_INVALID, "points missing");
-  if (N >= ((int64_t)1 << 31)) return fail(CLC_ERR_INVALID, "too many frames");
+// ---- creation from host data: shell (allocations + the small arrays) -> pipelined point upload -> finish ----------------
 
+namespace {
+
+// one shard's worth of the caller's data (all host pointers)
+struct HostSource {
+  int64_t n_frames = 0;
+  const double* frame_pose = nullptr;          // [n_frames*7]
+  const int64_t* offsets = nullptr;            // [n_frames+1] prefix local to the shard (offsets[0] == 0)
+  const double* const* frame_points = nullptr; // gather: [n_frames] arrays of AoS xyz ...
+  const double* flat = nullptr;                // ... or one flat AoS xyz array
+  const double* edge_points = nullptr;         // [n_frames*6] or NULL
+};
+
+int create_shell(clc_problem** out, const HostSource& src, int use_loss, double cauchy_a, int device, UploadShard* us) {
+  *out = nullptr;
+  const int64_t N = src.n_frames;
+  const int64_t P = N > 0 ? src.offsets[N] : 0;
   clc_problem* p = new clc_problem();
-  int rc = init_device(p, d->device);
+  int rc = init_device(p, device);
   if (rc != CLC_OK) { clc_problem_destroy(p); return rc; }
   p->n_frames = N;
   p->n_points = P;
-  p->n_edges = d->edge_points ? 2 * N : 0;
-  p->use_loss = d->use_loss;
-  p->cauchy_a = d->cauchy_a;
+  p->n_edges = src.edge_points ? 2 * N : 0;
+  p->use_loss = use_loss;
+  p->cauchy_a = cauchy_a;
   auto body = [&]() -> int {
-    int rc2 = alloc_points(p, /*with_z=*/true);
+    // the z stream is created only if a z != 0 turns up (pack path) -- a pinned flat source is laid out by the device
+    // kernel that also checks planarity, which needs it from the start
+    int rc2 = alloc_points(p, /*with_z=*/false);
     if (rc2 != CLC_OK) return rc2;
     CLC_CUDA(cudaMallocAsync(&p->frame_pose, sizeof(double) * 7 * std::max<int64_t>(N, 1), p->stream));
     CLC_CUDA(cudaMallocAsync(&p->plane, sizeof(double) * 4 * std::max<int64_t>(N, 1), p->stream));
     CLC_CUDA(cudaMallocAsync(&p->offsets, sizeof(int64_t) * (N + 1), p->stream));
     if (N > 0) {
-      CLC_CUDA(cudaMemcpyAsync(p->frame_pose, d->frame_pose, sizeof(double) * 7 * N, cudaMemcpyHostToDevice, p->stream));
-      CLC_CUDA(cudaMemcpyAsync(p->offsets, d->offsets, sizeof(int64_t) * (N + 1), cudaMemcpyHostToDevice, p->stream));
+      CLC_CUDA(cudaMemcpyAsync(p->frame_pose, src.frame_pose, sizeof(double) * 7 * N, cudaMemcpyHostToDevice, p->stream));
+      CLC_CUDA(cudaMemcpyAsync(p->offsets, src.offsets, sizeof(int64_t) * (N + 1), cudaMemcpyHostToDevice, p->stream));
     } else {
       CLC_CUDA(cudaMemsetAsync(p->offsets, 0, sizeof(int64_t), p->stream));
     }
@@ -643,32 +664,82 @@ int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
       CLC_CUDA(cudaMallocAsync(&p->edge_plane, sizeof(double) * 4 * p->n_edges, p->stream));
       CLC_CUDA(cudaMallocAsync(&p->edge_pt, sizeof(double) * 3 * p->n_edges, p->stream));
       // [n_frames*6] front,back == [n_edges*3]
-      CLC_CUDA(cudaMemcpyAsync(p->edge_pt, d->edge_points, sizeof(double) * 3 * p->n_edges, cudaMemcpyHostToDevice, p->stream));
+      CLC_CUDA(cudaMemcpyAsync(p->edge_pt, src.edge_points, sizeof(double) * 3 * p->n_edges, cudaMemcpyHostToDevice, p->stream));
     }
-    // points: AoS on the host -> staged in chunks -> SoA in HBM
-    if (P > 0) {
-      const int64_t chunk = std::min<int64_t>(P, (int64_t)8 << 20);  // 8 Mi points = 192 MiB of AoS per stage
-      double* stage = nullptr;
-      CLC_CUDA(cudaMallocAsync(&stage, sizeof(double) * 3 * chunk, p->stream));
-      int status = CLC_OK;
-      for (int64_t b = 0; b < P && status == CLC_OK; b += chunk) {
-        const int64_t n = std::min(chunk, P - b);
-        cudaError_t e = cudaMemcpyAsync(stage, d->points + 3 * b, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, p->stream);
-        if (e != cudaSuccess) { status = fail(CLC_ERR_CUDA, cudaGetErrorString(e)); break; }
-        clc::clc_aos_to_soa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, p->stream>>>(stage, n, p->x, p->y, p->z, b, p->d_nonplanar);
-        g_launches.fetch_add(1);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) status = fail(CLC_ERR_CUDA, cudaGetErrorString(e));
-      }
-      cudaStreamSynchronize(p->stream);
-      cudaFreeAsync(stage, p->stream);
-      if (status != CLC_OK) return status;
-    }
-    return finish_create(p);
+    return CLC_OK;
   };
   rc = body();
   if (rc != CLC_OK) { clc_problem_destroy(p); return rc; }
+  us->p = p;
+  us->frame_points = src.frame_points;
+  us->flat = src.flat;
+  us->offsets = src.offsets;
+  us->n_frames = N;
   *out = p;
+  return CLC_OK;
+}
+
+int validate_offsets(int64_t N, const int64_t* offsets) {
+  if (N > 0 && offsets[0] != 0) return fail(CLC_ERR_INVALID, "offsets[0] must be 0");
+  for (int64_t f = 0; f < N; ++f)
+    if (offsets[f + 1] < offsets[f]) return fail(CLC_ERR_INVALID, "offsets must be non-decreasing");
+  if (N >= ((int64_t)1 << 31)) return fail(CLC_ERR_INVALID, "too many frames");
+  return CLC_OK;
+}
+
+// uploads and finishes a set of freshly created shells; destroys all of them on failure
+int upload_and_finish(std::vector<clc_problem*>& problems, std::vector<UploadShard>& shards) {
+  int rc = upload_points(shards);
+  for (size_t g = 0; g < problems.size() && rc == CLC_OK; ++g) {
+    cudaSetDevice(problems[g]->device);
+    rc = finish_create(problems[g]);
+  }
+  if (rc != CLC_OK) {
+    const std::string msg = g_last_error;
+    for (clc_problem* p : problems) clc_problem_destroy(p);
+    problems.clear();
+    g_last_error = msg;
+  }
+  return rc;
+}
+
+}  // namespace
+
+int clc_problem_create(clc_problem** out, const clc_problem_desc* d) {
+  if (!out || !d) return fail(CLC_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (d->n_frames < 0 || (d->n_frames > 0 && (!d->frame_pose || !d->offsets)))
+    return fail(CLC_ERR_INVALID, "frame_pose/offsets missing");
+  if (!(d->cauchy_a > 0.0)) return fail(CLC_ERR_INVALID, "cauchy_a must be positive");
+  const int64_t N = d->n_frames;
+  int rc = validate_offsets(N, d->offsets);
+  if (rc != CLC_OK) return rc;
+  if (N > 0 && d->offsets[N] > 0 && !d->points) return fail(CLC_ERR_INVALID, "points missing");
+  const int64_t zero = 0;
+  HostSource src;
+  src.n_frames = N;
+  src.frame_pose = d->frame_pose;
+  src.offsets = N > 0 ? d->offsets : &zero;
+  src.flat = d->points;
+  src.edge_points = d->edge_points;
+  std::vector<clc_problem*> ps(1, nullptr);
+  std::vector<UploadShard> us(1);
+  rc = create_shell(&ps[0], src, d->use_loss, d->cauchy_a, d->device, &us[0]);
+  if (rc != CLC_OK) return rc;
+  rc = upload_and_finish(ps, us);
+  if (rc != CLC_OK) return rc;
+  *out = ps[0];
+  return CLC_OK;
+}
+
+int clc_problem_create_gather(clc_problem** out, const clc_gather_desc* d) {
+  if (!out || !d) return fail(CLC_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  clc_group* g = nullptr;
+  const int device = d->device;
+  int rc = clc_group_create_gather(&g, d, &device, 1);
+  if (rc != CLC_OK) return rc;
+  *out = group_release_single(g);
   return CLC_OK;
 }
 
@@ -812,24 +883,54 @@ int clc_problem_download(const clc_problem* p, double* frame_pose, int64_t* offs
 }
 
 // ---- evaluation -------------------------------------------------------------------------------------------------
+// Every collective operation is split into an enqueue phase and a wait phase, so that ONE host thread can drive the
+// shards of an in-process multi-GPU group: enqueue on every device first (the fused exchange makes block 0 of every
+// device's kernel wait for its peers' kernels), then wait for all of them.
 
-static int eval_common(clc_problem* p, const double pose7[7], bool loss, bool edges, int mode, int count) {
+static int eval_enqueue(clc_problem* p, const double pose7[7], bool loss, bool edges, int mode, int count) {
   int rc = set_device(p);
   if (rc != CLC_OK) return rc;
+  double* h_pose = p->pinned->pose;  // pinned: the copy below is truly asynchronous
   if (mode == clc::kModeLM) {
     if (!pose7) return fail(CLC_ERR_INVALID, "pose7 is NULL");
-    CLC_CUDA(cudaMemcpyAsync(p->pose, pose7, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
+    for (int i = 0; i < 7; ++i) h_pose[i] = pose7[i];
   } else {
     const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
-    CLC_CUDA(cudaMemcpyAsync(p->pose, ident, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
+    for (int i = 0; i < 7; ++i) h_pose[i] = ident[i];
   }
+  CLC_CUDA(cudaMemcpyAsync(p->pose, h_pose, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
   rc = launch_sweep(p, mode, loss, edges, p->pose, nullptr, nullptr);
   if (rc != CLC_OK) return rc;
   rc = allreduce_sums(p, count);
   if (rc != CLC_OK) return rc;
   CLC_CUDA(cudaMemcpyAsync(p->h_sums, p->sums, sizeof(double) * count, cudaMemcpyDeviceToHost, p->stream));
+  return CLC_OK;
+}
+
+static int eval_wait(clc_problem* p) {
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
   CLC_CUDA(cudaStreamSynchronize(p->stream));
   return check_p2p_error(p);
+}
+
+// runs one sweep on every shard of `ps` (a single problem, or the shards of a group); afterwards ps[0]->h_sums holds the
+// (all-reduced) sums
+static int eval_all(clc_problem* const* ps, int n, const double pose7[7], int which /*0 eval, 1 information, 2 closed form*/) {
+  int first_rc = CLC_OK;
+  for (int g = 0; g < n; ++g) {
+    clc_problem* p = ps[g];
+    int rc;
+    if (which == 0) rc = eval_enqueue(p, pose7, p->use_loss != 0, p->n_edges > 0, clc::kModeLM, clc::kNumSums);
+    else if (which == 1) rc = eval_enqueue(p, pose7, false, false, clc::kModeLM, clc::kNumSums);  // reference :318-381: no loss, no edges
+    else rc = eval_enqueue(p, nullptr, false, false, clc::kModeClosedForm, clc::kMaxOut);
+    if (rc != CLC_OK && first_rc == CLC_OK) first_rc = rc;
+  }
+  for (int g = 0; g < n; ++g) {
+    const int rc = eval_wait(ps[g]);
+    if (rc != CLC_OK && first_rc == CLC_OK) first_rc = rc;
+  }
+  return first_rc;
 }
 
 static void unpack_H(const double* sums, double* H36) {
@@ -842,27 +943,18 @@ static void unpack_H(const double* sums, double* H36) {
     }
 }
 
-int clc_eval(clc_problem* p, const double pose7[7], double H36[36], double g6[6], double* cost) {
-  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
-  int rc = eval_common(p, pose7, p->use_loss != 0, p->n_edges > 0, clc::kModeLM, clc::kNumSums);
-  if (rc != CLC_OK) return rc;
-  if (H36) unpack_H(p->h_sums, H36);
-  if (g6) for (int i = 0; i < 6; ++i) g6[i] = p->h_sums[21 + i];
-  if (cost) *cost = p->h_sums[27];
-  return CLC_OK;
+static void eval_post(const double* sums, double H36[36], double g6[6], double* cost) {
+  if (H36) unpack_H(sums, H36);
+  if (g6) for (int i = 0; i < 6; ++i) g6[i] = sums[21 + i];
+  if (cost) *cost = sums[27];
 }
 
-int clc_information(clc_problem* p, const double pose7[7], double H36[36], double b6[6], double* chi, double sv6[6],
-                    double V36[36]) {
-  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
-  // reference :318-381: no loss, no edge residuals, scale kept
-  int rc = eval_common(p, pose7, false, false, clc::kModeLM, clc::kNumSums);
-  if (rc != CLC_OK) return rc;
+static void information_post(const double* sums, double H36[36], double b6[6], double* chi, double sv6[6], double V36[36]) {
   double H[36];
-  unpack_H(p->h_sums, H);
+  unpack_H(sums, H);
   if (H36) std::memcpy(H36, H, sizeof(H));
-  if (b6) for (int i = 0; i < 6; ++i) b6[i] = -p->h_sums[21 + i];
-  if (chi) *chi = 2.0 * p->h_sums[27];
+  if (b6) for (int i = 0; i < 6; ++i) b6[i] = -sums[21 + i];
+  if (chi) *chi = 2.0 * sums[27];
   if (sv6 || V36) {
     // H is symmetric: singular values = |eigenvalues|, right singular vectors = eigenvectors (Eigen::JacobiSVD, :366)
     double w[6], V[36];
@@ -875,22 +967,18 @@ int clc_information(clc_problem* p, const double pose7[7], double H36[36], doubl
         for (int r = 0; r < 6; ++r) V36[r * 6 + c] = V[r * 6 + order[c]];
     }
   }
-  return CLC_OK;
 }
 
-int clc_closed_form(clc_problem* p, double Tlc[16], int* unobservable, double AtA81[81], double Atb9[9]) {
-  if (!p || !Tlc) return fail(CLC_ERR_INVALID, "NULL argument");
-  int rc = eval_common(p, nullptr, false, false, clc::kModeClosedForm, clc::kMaxOut);
-  if (rc != CLC_OK) return rc;
+static void closed_form_post(const double* sums, double Tlc[16], int* unobservable, double AtA81[81], double Atb9[9]) {
   double AtA[81], Atb[9];
   int k = 0;
   for (int i = 0; i < 9; ++i)
     for (int j = i; j < 9; ++j) {
-      AtA[i * 9 + j] = p->h_sums[k];
-      AtA[j * 9 + i] = p->h_sums[k];
+      AtA[i * 9 + j] = sums[k];
+      AtA[j * 9 + i] = sums[k];
       ++k;
     }
-  for (int i = 0; i < 9; ++i) Atb[i] = p->h_sums[45 + i];
+  for (int i = 0; i < 9; ++i) Atb[i] = sums[45 + i];
   if (AtA81) std::memcpy(AtA81, AtA, sizeof(AtA));
   if (Atb9) std::memcpy(Atb9, Atb, sizeof(Atb));
   double sv[9];
@@ -929,64 +1017,104 @@ int clc_closed_form(clc_problem* p, double Tlc[16], int* unobservable, double At
     Tlc[r * 4 + 3] = tlc[r];
   }
   Tlc[15] = 1.0;
+}
+
+int clc_eval(clc_problem* p, const double pose7[7], double H36[36], double g6[6], double* cost) {
+  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
+  int rc = eval_all(&p, 1, pose7, 0);
+  if (rc != CLC_OK) return rc;
+  eval_post(p->h_sums, H36, g6, cost);
+  return CLC_OK;
+}
+
+int clc_information(clc_problem* p, const double pose7[7], double H36[36], double b6[6], double* chi, double sv6[6],
+                    double V36[36]) {
+  if (!p) return fail(CLC_ERR_INVALID, "NULL problem");
+  int rc = eval_all(&p, 1, pose7, 1);
+  if (rc != CLC_OK) return rc;
+  information_post(p->h_sums, H36, b6, chi, sv6, V36);
+  return CLC_OK;
+}
+
+int clc_closed_form(clc_problem* p, double Tlc[16], int* unobservable, double AtA81[81], double Atb9[9]) {
+  if (!p || !Tlc) return fail(CLC_ERR_INVALID, "NULL argument");
+  int rc = eval_all(&p, 1, nullptr, 2);
+  if (rc != CLC_OK) return rc;
+  closed_form_post(p->h_sums, Tlc, unobservable, AtA81, Atb9);
   return CLC_OK;
 }
 
 // ---- the on-device LM solve ------------------------------------------------------------------------------------
 
-int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, clc_lm_summary* summary,
-                 clc_lm_iteration* trace, int trace_cap) {
-  if (!p || !pose7) return fail(CLC_ERR_INVALID, "NULL argument");
+namespace {
+
+struct SolveCtx {
+  clc_lm_options opt;
+  int max_sweeps = 0;
+  int launched = 0;
+  bool fused_update = true, loss = true, edges = false;
+};
+
+int solve_begin(clc_problem* p, const double pose7[7], const clc_lm_options& opt, SolveCtx* ctx) {
   int rc = set_device(p);
   if (rc != CLC_OK) return rc;
-  clc_lm_options opt;
-  if (opt_in) opt = *opt_in; else clc_lm_default_options(&opt);
-  if (opt.max_num_iterations < 0) return fail(CLC_ERR_INVALID, "max_num_iterations < 0");
-  if (opt.iterations_per_sync < 1) opt.iterations_per_sync = 1;
-
+  ctx->opt = opt;
   clc::lm_init(&p->h_lm->core, pose7, opt);
   if (!p->ev0) CLC_CUDA(cudaEventCreate(&p->ev0));  // kept for the life of the problem (destroyed with it)
   if (!p->ev1) CLC_CUDA(cudaEventCreate(&p->ev1));
-  cudaEvent_t ev0 = p->ev0, ev1 = p->ev1;
+  if (p->p2p_error) CLC_CUDA(cudaMemsetAsync(p->p2p_error, 0, sizeof(int), p->stream));  // a fresh solve starts clean
   CLC_CUDA(cudaMemcpyAsync(&p->lm->core, &p->h_lm->core, sizeof(clc::LmCore), cudaMemcpyHostToDevice, p->stream));
-  CLC_CUDA(cudaEventRecord(ev0, p->stream));
-  const bool fused_update = (p->nranks <= 1) || p->allreduce_mode == 1;
-  const bool loss = p->use_loss != 0, edges = p->n_edges > 0;
+  CLC_CUDA(cudaEventRecord(p->ev0, p->stream));
+  ctx->fused_update = (p->nranks <= 1) || p->allreduce_mode == 1;
+  ctx->loss = p->use_loss != 0;
+  ctx->edges = p->n_edges > 0;
   // every LM iteration needs exactly one sweep; invalid steps need none -> at most max_iterations + 1 sweeps
-  const int max_sweeps = opt.max_num_iterations + 2;
-  int launched = 0;
+  ctx->max_sweeps = opt.max_num_iterations + 2;
+  ctx->launched = 0;
   *p->h_done = 0;
-  while (launched < max_sweeps) {
-    const int batch = std::min(opt.iterations_per_sync, max_sweeps - launched);
-    for (int i = 0; i < batch; ++i) {
-      // fused mode: one kernel per LM iteration, chained with programmatic dependent launch (the next sweep prefetches
-      // its first stages while this one's block 0 reduces and updates)
-      rc = launch_sweep(p, clc::kModeLM, loss, edges, p->lm->core.cand, &p->lm->core.done, fused_update ? p->lm : nullptr,
-                        /*collective=*/true, /*pdl=*/fused_update && p->use_pdl);
-      if (rc != CLC_OK) return rc;
-      if (!fused_update) {
-        rc = allreduce_sums(p, clc::kNumSums);
-        if (rc != CLC_OK) return rc;
-        clc::clc_lm_kernel<<<1, 32, 0, p->stream>>>(p->lm, p->sums);
-        CLC_LAUNCH_CHECK();
-      }
-    }
-    launched += batch;
-    CLC_CUDA(cudaMemcpyAsync(p->h_done, &p->lm->core.done, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-    CLC_CUDA(cudaStreamSynchronize(p->stream));
-    if (*p->h_done != 0) break;
+  return CLC_OK;
+}
+
+// one LM iteration: the fused sweep (+ NCCL all-reduce and the LM kernel when the exchange is not fused)
+int solve_launch_one(clc_problem* p, SolveCtx* ctx) {
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  // fused mode: one kernel per LM iteration, chained with programmatic dependent launch (the next sweep prefetches
+  // its first stages while this one's block 0 reduces and updates)
+  rc = launch_sweep(p, clc::kModeLM, ctx->loss, ctx->edges, p->lm->core.cand, &p->lm->core.done,
+                    ctx->fused_update ? p->lm : nullptr, /*collective=*/true, /*pdl=*/ctx->fused_update && p->use_pdl);
+  if (rc != CLC_OK) return rc;
+  if (!ctx->fused_update) {
+    rc = allreduce_sums(p, clc::kNumSums);
+    if (rc != CLC_OK) return rc;
+    clc::clc_lm_kernel<<<1, 32, 0, p->stream>>>(p->lm, p->sums);
+    CLC_LAUNCH_CHECK();
   }
-  CLC_CUDA(cudaEventRecord(ev1, p->stream));
+  ctx->launched++;
+  return CLC_OK;
+}
+
+int solve_poll_enqueue(clc_problem* p) {
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  CLC_CUDA(cudaMemcpyAsync(p->h_done, &p->lm->core.done, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+  return CLC_OK;
+}
+
+int solve_finish(clc_problem* p, double pose7[7], clc_lm_summary* summary, clc_lm_iteration* trace, int trace_cap) {
+  int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  CLC_CUDA(cudaEventRecord(p->ev1, p->stream));
   CLC_CUDA(cudaMemcpyAsync(p->h_lm, p->lm, sizeof(clc::LmState), cudaMemcpyDeviceToHost, p->stream));
   CLC_CUDA(cudaStreamSynchronize(p->stream));
   float ms = 0.f;
-  CLC_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+  CLC_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
   rc = check_p2p_error(p);
   if (rc != CLC_OK) return rc;
-
   const clc::LmCore& s = p->h_lm->core;
   const clc_lm_iteration* dev_trace = p->h_lm->trace;
-  for (int i = 0; i < 7; ++i) pose7[i] = s.x[i];  // the last accepted point (a terminating candidate is not applied)
+  if (pose7)
+    for (int i = 0; i < 7; ++i) pose7[i] = s.x[i];  // the last accepted point (a terminating candidate is not applied)
   if (summary) {
     summary->termination = s.done ? s.done : CLC_TERM_NO_CONVERGENCE;
     summary->num_iterations = s.n_trace;
@@ -1003,6 +1131,66 @@ int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, 
     for (int i = 0; i < n; ++i) trace[i] = dev_trace[i];
   }
   return CLC_OK;
+}
+
+// the whole solve over the shards `ps` (n == 1: a plain problem, possibly one rank of a multi-process job)
+int solve_all(clc_problem* const* ps, int n, double pose7[7], const clc_lm_options* opt_in, clc_lm_summary* summary,
+              clc_lm_iteration* trace, int trace_cap) {
+  clc_lm_options opt;
+  if (opt_in) opt = *opt_in; else clc_lm_default_options(&opt);
+  if (opt.max_num_iterations < 0) return fail(CLC_ERR_INVALID, "max_num_iterations < 0");
+  if (opt.iterations_per_sync < 1) opt.iterations_per_sync = 1;
+  std::vector<SolveCtx> ctx((size_t)n);
+  int rc = CLC_OK;
+  for (int g = 0; g < n && rc == CLC_OK; ++g) rc = solve_begin(ps[g], pose7, opt, &ctx[g]);
+  if (rc != CLC_OK) return rc;
+  const int max_sweeps = ctx[0].max_sweeps;
+  int launched = 0;
+  while (launched < max_sweeps) {
+    const int batch = std::min(opt.iterations_per_sync, max_sweeps - launched);
+    // iteration-major order: sweep i of every shard is queued before sweep i+1 of any, so no device's queue can fill up
+    // with kernels that wait for a peer whose launches have not been issued yet
+    for (int i = 0; i < batch; ++i)
+      for (int g = 0; g < n; ++g) {
+        rc = solve_launch_one(ps[g], &ctx[g]);
+        if (rc != CLC_OK) return rc;
+      }
+    launched += batch;
+    for (int g = 0; g < n; ++g) {
+      rc = solve_poll_enqueue(ps[g]);
+      if (rc != CLC_OK) return rc;
+    }
+    bool all_done = true;
+    for (int g = 0; g < n; ++g) {
+      rc = set_device(ps[g]);
+      if (rc != CLC_OK) return rc;
+      CLC_CUDA(cudaStreamSynchronize(ps[g]->stream));
+      all_done = all_done && (*ps[g]->h_done != 0);
+    }
+    if (all_done) break;
+  }
+  double ms_max = 0.0;
+  int first_rc = CLC_OK;
+  for (int g = n - 1; g >= 0; --g) {  // shard 0 last: its pose / summary / trace are the ones returned (all shards agree)
+    clc_lm_summary sg;
+    rc = solve_finish(ps[g], g == 0 ? pose7 : nullptr, &sg, g == 0 ? trace : nullptr, trace_cap);
+    if (rc != CLC_OK && first_rc == CLC_OK) first_rc = rc;
+    if (rc == CLC_OK) {
+      ms_max = std::max(ms_max, sg.device_ms);
+      if (g == 0 && summary) *summary = sg;
+    }
+  }
+  if (first_rc != CLC_OK) return first_rc;
+  if (summary) summary->device_ms = ms_max;
+  return CLC_OK;
+}
+
+}  // namespace
+
+int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt_in, clc_lm_summary* summary,
+                 clc_lm_iteration* trace, int trace_cap) {
+  if (!p || !pose7) return fail(CLC_ERR_INVALID, "NULL argument");
+  return solve_all(&p, 1, pose7, opt_in, summary, trace, trace_cap);
 }
 
 // ---- LineFittingCeres, batched ------------------------------------------------------------------------------------
@@ -1234,8 +1422,9 @@ int clc_comm_p2p_import(clc_comm* c, const void* handles) {
 int clc_comm_destroy(clc_comm* c) {
   if (!c) return CLC_OK;
   cudaSetDevice(c->device);
-  for (int r = 0; r < c->nranks; ++r)
-    if (r != c->rank && c->peer_block[r]) cudaIpcCloseMemHandle(c->peer_block[r]);
+  if (!c->local)
+    for (int r = 0; r < c->nranks; ++r)
+      if (r != c->rank && c->peer_block[r]) cudaIpcCloseMemHandle(c->peer_block[r]);
   if (c->p2p_block) cudaFree(c->p2p_block);
   if (c->comm && nccl_api()->handle) {
     cudaSetDevice(c->device);
@@ -1270,6 +1459,312 @@ int clc_problem_set_allreduce_mode(clc_problem* p, int mode) {
   if (mode == 1 && !(p->comm_obj && p->comm_obj->p2p_ready))
     return fail(CLC_ERR_STATE, "peer exchange not initialised (clc_comm_p2p_export / clc_comm_p2p_import)");
   p->allreduce_mode = mode;
+  return CLC_OK;
+}
+
+// ---- in-process multi-GPU: one host thread, G devices, the same fused NVLink exchange --------------------------------
+
+struct clc_group {
+  std::vector<clc_problem*> problems;
+  std::vector<clc_comm*> comms;  // local communicators (empty for a single device)
+  int64_t n_frames = 0, n_points = 0;
+};
+
+}  // extern "C"
+static clc_problem* group_release_single(clc_group* g) {
+  clc_problem* p = g->problems.empty() ? nullptr : g->problems[0];
+  delete g;
+  return p;
+}
+extern "C" {
+
+namespace {
+
+// mailboxes on every device, peer access between all pairs, plain device pointers instead of IPC handles
+int comms_create_local(std::vector<clc_comm*>* out, const int* devices, int n) {
+  if (n > clc::kMaxRanks) return fail(CLC_ERR_INVALID, "too many devices for the peer exchange");
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return fail(CLC_ERR_INVALID, "a device may appear only once in a group");
+  auto cleanup = [&]() {
+    for (clc_comm* c : *out) clc_comm_destroy(c);
+    out->clear();
+  };
+  for (int i = 0; i < n; ++i) {
+    clc_comm* c = new clc_comm();
+    c->nranks = n;
+    c->rank = i;
+    c->device = devices[i];
+    c->local = true;
+    out->push_back(c);
+    cudaError_t e = cudaSetDevice(devices[i]);
+    if (e == cudaSuccess) e = cudaMalloc(&c->p2p_block, c->block_bytes());
+    if (e == cudaSuccess) e = cudaMemset(c->p2p_block, 0, c->block_bytes());
+    if (e != cudaSuccess) {
+      cleanup();
+      return fail(CLC_ERR_CUDA, std::string("group mailbox: ") + cudaGetErrorString(e));
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    cudaSetDevice(devices[i]);
+    for (int j = 0; j < n; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      cudaError_t e = cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+      if (e == cudaSuccess && !can) {
+        cleanup();
+        return fail(CLC_ERR_CUDA, "devices " + std::to_string(devices[i]) + " and " + std::to_string(devices[j]) +
+                                      " have no peer access: the fused exchange needs NVLink/PCIe P2P");
+      }
+      if (e == cudaSuccess) e = cudaDeviceEnablePeerAccess(devices[j], 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      if (e != cudaSuccess) {
+        cleanup();
+        return fail(CLC_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    for (int r = 0; r < n; ++r) (*out)[i]->peer_block[r] = (*out)[r]->p2p_block;
+    (*out)[i]->p2p_ready = true;
+  }
+  return CLC_OK;
+}
+
+int group_attach(clc_group* g, const int* devices, int n) {
+  if (n <= 1) return CLC_OK;
+  int rc = comms_create_local(&g->comms, devices, n);
+  if (rc != CLC_OK) return rc;
+  for (int i = 0; i < n; ++i) {
+    rc = clc_problem_attach_comm(g->problems[i], g->comms[i]);
+    if (rc != CLC_OK) return rc;
+  }
+  // warm the peer mappings and the exchange path: a few collective sweeps outside any timed region
+  const double ident[7] = {0, 0, 0, 0, 0, 0, 1};
+  for (int k = 0; k < 3 && rc == CLC_OK; ++k) rc = eval_all(g->problems.data(), n, ident, 1);
+  return rc;
+}
+
+int resolve_devices(const int* devices, int n_devices, std::vector<int>* out) {
+  int count = 0;
+  CLC_CUDA(cudaGetDeviceCount(&count));
+  if (count <= 0) return fail(CLC_ERR_CUDA, "no CUDA device");
+  if (n_devices < 1 || !devices) return fail(CLC_ERR_INVALID, "need at least one device");
+  for (int i = 0; i < n_devices; ++i) {
+    int d = devices[i];
+    if (d < 0) CLC_CUDA(cudaGetDevice(&d));
+    if (d >= count) return fail(CLC_ERR_INVALID, "device ordinal out of range");
+    out->push_back(d);
+  }
+  return CLC_OK;
+}
+
+}  // namespace
+
+int clc_group_destroy(clc_group* g) {
+  if (!g) return CLC_OK;
+  for (clc_problem* p : g->problems) clc_problem_destroy(p);
+  for (clc_comm* c : g->comms) clc_comm_destroy(c);
+  delete g;
+  return CLC_OK;
+}
+
+int clc_group_create_gather(clc_group** out, const clc_gather_desc* d, const int* devices, int n_devices) {
+  if (!out || !d) return fail(CLC_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  const int64_t N = d->n_frames;
+  if (N < 0 || (N > 0 && (!d->frame_pose || !d->frame_points || !d->frame_counts)))
+    return fail(CLC_ERR_INVALID, "frame_pose/frame_points/frame_counts missing");
+  if (!(d->cauchy_a > 0.0)) return fail(CLC_ERR_INVALID, "cauchy_a must be positive");
+  if (N >= ((int64_t)1 << 31)) return fail(CLC_ERR_INVALID, "too many frames");
+  std::vector<int> devs;
+  int rc = resolve_devices(devices, n_devices, &devs);
+  if (rc != CLC_OK) return rc;
+  const int G = (int)devs.size();
+  std::vector<int64_t> prefix((size_t)N + 1, 0);
+  for (int64_t f = 0; f < N; ++f) {
+    if (d->frame_counts[f] < 0) return fail(CLC_ERR_INVALID, "negative frame count");
+    if (d->frame_counts[f] > 0 && !d->frame_points[f]) return fail(CLC_ERR_INVALID, "NULL frame_points entry");
+    prefix[f + 1] = prefix[f] + d->frame_counts[f];
+  }
+  clc_group* g = new clc_group();
+  g->n_frames = N;
+  g->n_points = prefix[N];
+  std::vector<UploadShard> shards((size_t)G);
+  std::vector<std::vector<int64_t>> local_offsets((size_t)G);
+  for (int i = 0; i < G && rc == CLC_OK; ++i) {
+    int64_t fb = 0, fe = N;
+    rc = clc_shard_range(N, prefix.data(), G, i, &fb, &fe);  // contiguous frame ranges balanced by point count
+    if (rc != CLC_OK) break;
+    std::vector<int64_t>& lo = local_offsets[i];
+    lo.resize((size_t)(fe - fb) + 1);
+    for (int64_t f = fb; f <= fe; ++f) lo[f - fb] = prefix[f] - prefix[fb];
+    HostSource src;
+    src.n_frames = fe - fb;
+    src.frame_pose = d->frame_pose + 7 * fb;
+    src.offsets = lo.data();
+    src.frame_points = d->frame_points + fb;
+    src.edge_points = d->edge_points ? d->edge_points + 6 * fb : nullptr;
+    clc_problem* p = nullptr;
+    rc = create_shell(&p, src, d->use_loss, d->cauchy_a, devs[i], &shards[i]);
+    if (rc == CLC_OK) g->problems.push_back(p);
+  }
+  if (rc == CLC_OK) {
+    shards.resize(g->problems.size());
+    rc = upload_and_finish(g->problems, shards);
+  }
+  if (rc == CLC_OK) rc = group_attach(g, devs.data(), G);
+  if (rc != CLC_OK) {
+    const std::string msg = g_last_error;
+    clc_group_destroy(g);
+    g_last_error = msg;
+    return rc;
+  }
+  *out = g;
+  return CLC_OK;
+}
+
+int clc_group_create_synthetic(clc_group** out, const clc_synthetic_desc* d, const int* devices, int n_devices) {
+  if (!out || !d) return fail(CLC_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  std::vector<int> devs;
+  int rc = resolve_devices(devices, n_devices, &devs);
+  if (rc != CLC_OK) return rc;
+  const int G = (int)devs.size();
+  clc_group* g = new clc_group();
+  const int64_t fb0 = d->frame_begin, N = d->frame_end - d->frame_begin;
+  for (int i = 0; i < G && rc == CLC_OK; ++i) {
+    clc_synthetic_desc di = *d;
+    di.frame_begin = fb0 + N * i / G;
+    di.frame_end = fb0 + N * (i + 1) / G;
+    di.device = devs[i];
+    clc_problem* p = nullptr;
+    rc = clc_problem_create_synthetic(&p, &di);
+    if (rc == CLC_OK) {
+      g->problems.push_back(p);
+      g->n_frames += p->n_frames;
+      g->n_points += p->n_points;
+    }
+  }
+  if (rc == CLC_OK) rc = group_attach(g, devs.data(), G);
+  if (rc != CLC_OK) {
+    const std::string msg = g_last_error;
+    clc_group_destroy(g);
+    g_last_error = msg;
+    return rc;
+  }
+  *out = g;
+  return CLC_OK;
+}
+
+int clc_group_size(const clc_group* g, int* n_devices, int64_t* n_frames, int64_t* n_points) {
+  if (!g) return fail(CLC_ERR_INVALID, "NULL group");
+  if (n_devices) *n_devices = (int)g->problems.size();
+  if (n_frames) *n_frames = g->n_frames;
+  if (n_points) *n_points = g->n_points;
+  return CLC_OK;
+}
+
+int clc_group_problem(clc_group* g, int index, clc_problem** out) {
+  if (!g || !out || index < 0 || index >= (int)g->problems.size()) return fail(CLC_ERR_INVALID, "bad group index");
+  *out = g->problems[index];
+  return CLC_OK;
+}
+
+int clc_group_eval(clc_group* g, const double pose7[7], double H36[36], double g6[6], double* cost) {
+  if (!g || g->problems.empty()) return fail(CLC_ERR_INVALID, "NULL group");
+  int rc = eval_all(g->problems.data(), (int)g->problems.size(), pose7, 0);
+  if (rc != CLC_OK) return rc;
+  eval_post(g->problems[0]->h_sums, H36, g6, cost);
+  return CLC_OK;
+}
+
+int clc_group_information(clc_group* g, const double pose7[7], double H36[36], double b6[6], double* chi, double sv6[6],
+                          double V36[36]) {
+  if (!g || g->problems.empty()) return fail(CLC_ERR_INVALID, "NULL group");
+  int rc = eval_all(g->problems.data(), (int)g->problems.size(), pose7, 1);
+  if (rc != CLC_OK) return rc;
+  information_post(g->problems[0]->h_sums, H36, b6, chi, sv6, V36);
+  return CLC_OK;
+}
+
+int clc_group_closed_form(clc_group* g, double Tlc16[16], int* unobservable, double AtA81[81], double Atb9[9]) {
+  if (!g || g->problems.empty() || !Tlc16) return fail(CLC_ERR_INVALID, "NULL argument");
+  int rc = eval_all(g->problems.data(), (int)g->problems.size(), nullptr, 2);
+  if (rc != CLC_OK) return rc;
+  closed_form_post(g->problems[0]->h_sums, Tlc16, unobservable, AtA81, Atb9);
+  return CLC_OK;
+}
+
+int clc_group_solve_lm(clc_group* g, double pose7[7], const clc_lm_options* opt, clc_lm_summary* summary,
+                       clc_lm_iteration* trace, int trace_cap) {
+  if (!g || g->problems.empty() || !pose7) return fail(CLC_ERR_INVALID, "NULL argument");
+  return solve_all(g->problems.data(), (int)g->problems.size(), pose7, opt, summary, trace, trace_cap);
+}
+
+// Devices the reference-facing drop-in uses (its signatures have no device argument): the environment variable
+// CLC_DEVICES = "0,1,2,3" | "all" | unset (the current device).
+int clc_default_devices(int* devices, int cap, int* n) {
+  if (!devices || !n || cap < 1) return fail(CLC_ERR_INVALID, "bad device list arguments");
+  int count = 0;
+  CLC_CUDA(cudaGetDeviceCount(&count));
+  if (count <= 0) return fail(CLC_ERR_CUDA, "no CUDA device");
+  *n = 0;
+  const char* env = std::getenv("CLC_DEVICES");
+  if (!env || !*env) {
+    int cur = 0;
+    CLC_CUDA(cudaGetDevice(&cur));
+    devices[(*n)++] = cur;
+    return CLC_OK;
+  }
+  if (std::strcmp(env, "all") == 0) {
+    for (int d = 0; d < count && *n < cap; ++d) devices[(*n)++] = d;
+    return CLC_OK;
+  }
+  const char* s = env;
+  while (*s) {
+    char* endp = nullptr;
+    const long v = std::strtol(s, &endp, 10);
+    if (endp == s) return fail(CLC_ERR_INVALID, std::string("cannot parse CLC_DEVICES=") + env);
+    if (v < 0 || v >= count) return fail(CLC_ERR_INVALID, std::string("CLC_DEVICES names a device that does not exist: ") + env);
+    if (*n < cap) devices[(*n)++] = (int)v;
+    s = endp;
+    while (*s == ',' || *s == ' ') ++s;
+  }
+  if (*n == 0) return fail(CLC_ERR_INVALID, "CLC_DEVICES is empty");
+  return CLC_OK;
+}
+
+// test hook (no CUDA involved): what the pack threads would write for the local point range [a, b) of a gathered shard.
+// xy != 0: packed x,y pairs, *nonplanar receives whether a z != 0 was met; xy == 0: packed xyz.
+int clc_debug_pack(int64_t n_frames, const double* const* frame_points, const int64_t* frame_counts, int64_t a, int64_t b,
+                   int xy, double* out, int* nonplanar) {
+  if (n_frames < 0 || !frame_points || !frame_counts || !out || a < 0 || b < a) return fail(CLC_ERR_INVALID, "bad pack arguments");
+  std::vector<int64_t> prefix((size_t)n_frames + 1, 0);
+  for (int64_t f = 0; f < n_frames; ++f) prefix[f + 1] = prefix[f] + frame_counts[f];
+  if (b > prefix[n_frames]) return fail(CLC_ERR_INVALID, "pack range beyond the last point");
+  UploadShard s;
+  s.frame_points = frame_points;
+  s.offsets = prefix.data();
+  s.n_frames = n_frames;
+  if (xy) {
+    const bool np = pack_xy(s, a, b, out);
+    if (nonplanar) *nonplanar = np ? 1 : 0;
+  } else {
+    pack_xyz(s, a, b, out);
+  }
+  return CLC_OK;
+}
+
+// statistics of the most recent host -> HBM upload of this process (measurement hook)
+int clc_upload_last_stats(double* total_ms, double* pack_wait_ms, int64_t* bytes_h2d, int* chunks, int* pack_threads,
+                          int* direct) {
+  if (total_ms) *total_ms = g_last_upload.total_ms;
+  if (pack_wait_ms) *pack_wait_ms = g_last_upload.pack_wait_ms;
+  if (bytes_h2d) *bytes_h2d = g_last_upload.bytes_h2d;
+  if (chunks) *chunks = g_last_upload.chunks;
+  if (pack_threads) *pack_threads = g_last_upload.threads;
+  if (direct) *direct = g_last_upload.direct;
   return CLC_OK;
 }
 
@@ -1341,6 +1836,35 @@ int clc_debug_sweep_timing(clc_problem* p, const double pose7[7], int with_lm, i
   if (e != cudaSuccess) return fail(CLC_ERR_CUDA, cudaGetErrorString(e));
   return CLC_OK;
 }
+
+int clc_bench_h2d(int64_t bytes, int device, int reps, float* ms_each) {
+  if (bytes < 1 || reps < 1 || !ms_each) return fail(CLC_ERR_INVALID, "bad h2d bench arguments");
+  if (device >= 0) CLC_CUDA(cudaSetDevice(device));
+  void *h = nullptr, *d = nullptr;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaHostAlloc(&h, (size_t)bytes, cudaHostAllocDefault);
+  if (e == cudaSuccess) { std::memset(h, 0, (size_t)bytes); e = cudaMalloc(&d, (size_t)bytes); }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  for (int i = -1; i < reps && e == cudaSuccess; ++i) {  // one untimed copy first
+    e = cudaEventRecord(e0, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, (size_t)bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && i >= 0) e = cudaEventElapsedTime(&ms_each[i], e0, e1);
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (st) cudaStreamDestroy(st);
+  if (d) cudaFree(d);
+  if (h) cudaFreeHost(h);
+  if (e != cudaSuccess) return fail(CLC_ERR_CUDA, std::string("h2d bench: ") + cudaGetErrorString(e));
+  return CLC_OK;
+}
+
+int64_t clc_solve_readback_bytes(void) { return (int64_t)sizeof(clc::LmState) + (int64_t)sizeof(int); }
 
 int clc_host_alloc(void** ptr, int64_t bytes) {
   if (!ptr || bytes < 0) return fail(CLC_ERR_INVALID, "bad host alloc arguments");

@@ -339,8 +339,8 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   // tail of the previous sweep (final reduce + LM update on its block 0).  From here on the pose, the `done` flag,
   // the partial sums and the ticket of the previous launch are needed: wait for it to complete.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (args.done != nullptr && *args.done != 0) {
-    // the LM finished: nothing to do, but the bulk copies already in flight must land before the block may exit
+  if (args.done != nullptr && (*args.done != 0 || (args.error != nullptr && *args.error != 0))) {
+    // the LM finished (or an earlier sweep of this solve lost a peer): nothing to do, but the bulk copies already in flight must land before the block may exit
     const int issued = n_chunks < NST ? n_chunks : NST;
     for (int c = 0; c < issued; ++c) mbar_wait(bars + c, 0u);
     return;
@@ -581,7 +581,20 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (blockIdx.x != 0) return;
   if (threadIdx.x == 0) {
+    // The grid is sized to be fully co-resident (one block per SM), which is what lets block 0 wait here.  Should that ever
+    // not hold (MPS with a reduced SM share, a foreign kernel pinning SMs), fail loudly instead of hanging: after 2 s the
+    // error flag is raised, the host reports it and the LM is stopped.
+    unsigned int polls = 0;
+    unsigned long long t0 = 0;
     while (ld_acquire_gpu(args.ticket) != gridDim.x) {
+      if ((++polls & 0x3ffu) == 0u) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) {
+          if (args.error != nullptr) *args.error = 2;
+          break;
+        }
+      }
     }
   }
   __syncthreads();
@@ -668,7 +681,12 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
       if (threadIdx.x == 0) {
         double sums[kNumSums];
         for (int k = 0; k < kNumSums; ++k) sums[k] = s_red[0][k];
-        lm_update(reinterpret_cast<LmCore*>(s_core), args.lm->trace, sums);
+        if (args.error != nullptr && *args.error != 0) {
+          // a peer never answered / the grid was not co-resident: the sums are not the whole problem's -- stop the solve
+          reinterpret_cast<LmCore*>(s_core)->done = CLC_TERM_FAILURE;
+        } else {
+          lm_update(reinterpret_cast<LmCore*>(s_core), args.lm->trace, sums);
+        }
       }
       __syncthreads();
       unsigned long long* o_core = reinterpret_cast<unsigned long long*>(&args.lm->core);
@@ -704,6 +722,19 @@ __global__ void clc_aos_to_soa_kernel(const double* __restrict__ aos, int64_t n,
     off_plane = !(zi == 0.0);
   }
   if (__any_sync(0xffffffffu, off_plane) && (threadIdx.x & 31) == 0) atomicOr(nonplanar, 1);
+}
+
+// packed (x,y)[n] -> SoA: the upload format of planar data (the host packer checked every z == 0 and left it behind,
+// so 16 instead of 24 bytes per point cross PCIe)
+__global__ void clc_aos2_to_soa_kernel(const double2* __restrict__ xy, int64_t n, double* __restrict__ x,
+                                       double* __restrict__ y, double* __restrict__ z, int64_t dst_off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double2 v = xy[i];
+    x[dst_off + i] = v.x;
+    y[dst_off + i] = v.y;
+    if (z != nullptr) z[dst_off + i] = 0.0;
+  }
 }
 
 __global__ void clc_soa_to_aos_kernel(const double* __restrict__ x, const double* __restrict__ y,

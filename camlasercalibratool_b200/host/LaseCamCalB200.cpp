@@ -9,8 +9,10 @@
 //   host (here)   marshal std::vector<Oberserve> into the flat arrays of the C ABI (include/clc_b200.h)
 //   GPU (library) board planes, fused residual+Jacobian+Cauchy+reduce sweeps, the Ceres-equivalent LM loop with its
 //                 6x6 damped solve and SE(3) update, the un-robustified information matrix, the closed-form 9x9
-// There is no CPU fallback: if the library reports an error the functions print it and leave the output untouched
-// (the reference's functions are `void` and have no error channel, reference include/LaseCamCalCeres.h:26-29).
+// There is no CPU fallback: if the library reports an error the functions throw std::runtime_error (the reference's
+// functions are `void` with no error channel, reference include/LaseCamCalCeres.h:26-29; its own failures are exceptions).
+// Multi-GPU: the environment variable CLC_DEVICES ("0,1,2,3" or "all") spreads one call over several devices of this
+// process -- frames sharded by point count, 28 sums exchanged over NVLink inside the sweep kernel.
 #include "LaseCamCalCeres.h"
 
 #include <cmath>
@@ -18,67 +20,75 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "clc_b200.h"
 
 namespace {
 
+// Eigen::Vector3d is three contiguous doubles: the std::vector<Vector3d> of a frame IS the AoS xyz array the C ABI takes
+static_assert(sizeof(Eigen::Vector3d) == 3 * sizeof(double), "Vector3d must be three packed doubles");
+
+// The reference's functions are void and have no error channel (reference include/LaseCamCalCeres.h:26-29); its own
+// failure mode is a C++ exception (std::vector::at at src/LaseCamCalCeres.cpp:278-279, Eigen/Ceres asserts).  A failed
+// library call must not leave Tcl looking like a result, so it throws as well.
+[[noreturn]] void fail(const char* what) {
+  throw std::runtime_error(std::string("libclc_b200: ") + what + ": " + clc_last_error());
+}
+
+// No point is copied here: the library gathers the frames from where they lie (pack threads -> pinned ring -> PCIe).
 struct Marshalled {
-  std::vector<double> frame_pose;  // [N*7] qx qy qz qw tx ty tz
-  std::vector<int64_t> offsets;    // [N+1]
-  std::vector<double> points;      // [P*3]
-  std::vector<double> edge_points; // [N*6] or empty
+  std::vector<double> frame_pose;        // [N*7] qx qy qz qw tx ty tz
+  std::vector<const double*> frame_pts;  // [N] -> obs[i].points(.data()) or points_on_line
+  std::vector<int64_t> counts;           // [N]
+  std::vector<double> edge_points;       // [N*6] or empty
+  clc_gather_desc desc;
 };
 
 // Point-set selection of reference src/LaseCamCalCeres.cpp:233-237; edge points of :278-279 (only when both flags are
 // set, :258).
-Marshalled marshal(const std::vector<Oberserve>& obs, bool use_linefitting_data, bool use_boundary_constraint) {
-  Marshalled m;
+void marshal(const std::vector<Oberserve>& obs, bool use_linefitting_data, bool use_boundary_constraint, Marshalled* m) {
   const size_t n = obs.size();
-  m.frame_pose.resize(7 * n);
-  m.offsets.assign(n + 1, 0);
+  m->frame_pose.resize(7 * n);
+  m->frame_pts.resize(n);
+  m->counts.resize(n);
   const bool edges = use_boundary_constraint && use_linefitting_data;
-  if (edges) m.edge_points.assign(6 * n, 0.0);
-  size_t total = 0;
-  for (size_t i = 0; i < n; ++i) total += (use_linefitting_data ? obs[i].points_on_line : obs[i].points).size();
-  m.points.reserve(3 * total);
+  if (edges) m->edge_points.assign(6 * n, 0.0);
   for (size_t i = 0; i < n; ++i) {
     const Oberserve& ob = obs[i];
-    double* fp = &m.frame_pose[7 * i];
+    double* fp = &m->frame_pose[7 * i];
     fp[0] = ob.tagPose_Qca.x(); fp[1] = ob.tagPose_Qca.y(); fp[2] = ob.tagPose_Qca.z(); fp[3] = ob.tagPose_Qca.w();
     fp[4] = ob.tagPose_tca.x(); fp[5] = ob.tagPose_tca.y(); fp[6] = ob.tagPose_tca.z();
     const std::vector<Eigen::Vector3d>& pts = use_linefitting_data ? ob.points_on_line : ob.points;
-    for (const Eigen::Vector3d& p : pts) {
-      m.points.push_back(p.x()); m.points.push_back(p.y()); m.points.push_back(p.z());
-    }
-    m.offsets[i + 1] = m.offsets[i] + (int64_t)pts.size();
-    if (edges && !pts.empty() && !ob.points.empty()) {
-      const Eigen::Vector3d& a = ob.points.front();
-      const Eigen::Vector3d& b = ob.points.back();
-      double* e = &m.edge_points[6 * i];
+    m->frame_pts[i] = pts.empty() ? nullptr : reinterpret_cast<const double*>(pts.data());
+    m->counts[i] = (int64_t)pts.size();
+    if (edges) {
+      // the reference reads ob.points.at(0) / .at(size-1) for every frame (:278-279): an empty scan throws there too
+      const Eigen::Vector3d& a = ob.points.at(0);
+      const Eigen::Vector3d& b = ob.points.at(ob.points.size() - 1);
+      double* e = &m->edge_points[6 * i];
       e[0] = a.x(); e[1] = a.y(); e[2] = a.z(); e[3] = b.x(); e[4] = b.y(); e[5] = b.z();
     }
   }
-  return m;
+  m->desc.n_frames = (int64_t)n;
+  m->desc.frame_pose = m->frame_pose.data();
+  m->desc.frame_points = m->frame_pts.data();
+  m->desc.frame_counts = m->counts.data();
+  m->desc.edge_points = m->edge_points.empty() ? nullptr : m->edge_points.data();
+  m->desc.use_loss = 1;      // #define LOSSFUNCTION, reference :212
+  m->desc.cauchy_a = 0.05;   // reference :249
+  m->desc.device = -1;
 }
 
-clc_problem* create(const Marshalled& m) {
-  clc_problem_desc d;
-  d.n_frames = (int64_t)m.offsets.size() - 1;
-  d.frame_pose = m.frame_pose.data();
-  d.offsets = m.offsets.data();
-  d.points = m.points.data();
-  d.edge_points = m.edge_points.empty() ? nullptr : m.edge_points.data();
-  d.use_loss = 1;      // #define LOSSFUNCTION, reference :212
-  d.cauchy_a = 0.05;   // reference :249
-  d.device = -1;
-  clc_problem* p = nullptr;
-  if (clc_problem_create(&p, &d) != CLC_OK) {
-    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
-    return nullptr;
-  }
-  return p;
+// The devices of this process the solve is spread over: CLC_DEVICES = "0,1,..." | "all" | unset (current device).
+clc_group* create(const Marshalled& m) {
+  int devices[16], n_devices = 0;
+  if (clc_default_devices(devices, 16, &n_devices) != CLC_OK) fail("device selection");
+  clc_group* g = nullptr;
+  if (clc_group_create_gather(&g, &m.desc, devices, n_devices) != CLC_OK) fail("problem upload");
+  return g;
 }
 
 void print4(const double T[16]) {
@@ -100,17 +110,14 @@ const char* termination_name(int t) {
 
 // reference src/LaseCamCalCeres.cpp:112-203
 void CamLaserCalClosedSolution(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tlc) {
-  const Marshalled m = marshal(obs, /*use_linefitting_data=*/true, false);  // :143 uses points_on_line
-  clc_problem* p = create(m);
-  if (!p) return;
+  Marshalled m;
+  marshal(obs, /*use_linefitting_data=*/true, false, &m);  // :143 uses points_on_line
+  clc_group* g = create(m);
   double T[16];
   int unobservable = 0;
-  const int rc = clc_closed_form(p, T, &unobservable, nullptr, nullptr);
-  clc_problem_destroy(p);
-  if (rc != CLC_OK) {
-    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
-    return;
-  }
+  const int rc = clc_group_closed_form(g, T, &unobservable, nullptr, nullptr);
+  clc_group_destroy(g);
+  if (rc != CLC_OK) fail("closed form");
   if (unobservable) {  // :173-178
     std::cout << std::endl << "~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~~" << std::endl;
     std::cout << " Notice Notice Notice: system unobservable !!!!!!!" << std::endl;
@@ -129,18 +136,20 @@ void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl,
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 4; ++c) T[r * 4 + c] = Tcl(r, c);
   clc_T_to_pose7(T, pose);  // :215-219 (Eigen::Quaterniond(Matrix3d) restated in the library)
-  const Marshalled m = marshal(obs, use_linefitting_data, use_boundary_constraint);
-  clc_problem* p = create(m);
-  if (!p) return;
+  Marshalled m;
+  marshal(obs, use_linefitting_data, use_boundary_constraint, &m);
+  clc_group* p = create(m);
 
   clc_lm_options opt;
   clc_lm_default_options(&opt);  // DENSE_QR-equivalent step, max_num_iterations = 100 (:303-304), Ceres defaults
   clc_lm_summary sum;
   std::vector<clc_lm_iteration> trace(256);
-  if (clc_solve_lm(p, pose, &opt, &sum, trace.data(), (int)trace.size()) != CLC_OK) {
-    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
-    clc_problem_destroy(p);
-    return;
+  if (clc_group_solve_lm(p, pose, &opt, &sum, trace.data(), (int)trace.size()) != CLC_OK) {
+    clc_group_destroy(p);
+    fail("LM solve");
+  }
+  if (sum.termination == CLC_TERM_FAILURE) {  // Ceres would report FAILURE and leave the parameters at the start value
+    std::cout << "Termination: FAILURE (no usable step / non-finite evaluation); Tcl left unchanged" << std::endl;
   }
   // the counterpart of summary.FullReport() (:309)
   std::cout << "\nSolver Summary (libclc_b200, on-device Levenberg-Marquardt)\n";
@@ -161,7 +170,7 @@ void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl,
 
   // ---- analysis tail (:316-381) ----
   double H[36], b[6], chi = 0.0, sv[6], V[36];
-  if (clc_information(p, pose, H, b, &chi, sv, V) == CLC_OK) {
+  if (clc_group_information(p, pose, H, b, &chi, sv, V) == CLC_OK) {
     std::cout << "----- H singular values--------:\n";
     for (int i = 0; i < 6; ++i) std::cout << sv[i] << "\n";
     int n_null = 0;
@@ -177,9 +186,10 @@ void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl,
     }
     std::cout << "\nrecover chi2: " << chi / 2. << std::endl;  // :381
   } else {
-    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
+    clc_group_destroy(p);
+    fail("information matrix");
   }
-  clc_problem_destroy(p);
+  clc_group_destroy(p);
 }
 
 // reference src/LaseCamCalCeres.cpp:68-110 (pure host I/O; kept so that the translation unit stays a complete
@@ -189,13 +199,14 @@ void CalibrationTool_SavePlanePoints(const std::vector<Oberserve> obs, const Eig
   fs_planar << std::setprecision(3);
   fs_points << std::setprecision(3);
   fs_lines << std::setprecision(3);
-  const Marshalled m = marshal(obs, false, false);
-  clc_problem* p = create(m);
+  Marshalled m;
+  marshal(obs, false, false, &m);
+  clc_problem* p = nullptr;
+  if (clc_problem_create_gather(&p, &m.desc) != CLC_OK) fail("problem upload");
   std::vector<double> planes(4 * obs.size());
-  if (p) {
-    clc_problem_download(p, nullptr, nullptr, nullptr, nullptr, planes.data());
-    clc_problem_destroy(p);
-  }
+  const int rc = clc_problem_download(p, nullptr, nullptr, nullptr, nullptr, planes.data());
+  clc_problem_destroy(p);
+  if (rc != CLC_OK) fail("board planes");
   auto to_cam = [&](const Eigen::Vector3d& q, double out[3]) {
     for (int r = 0; r < 3; ++r) out[r] = Tcl(r, 0) * q.x() + Tcl(r, 1) * q.y() + Tcl(r, 2) * q.z() + Tcl(r, 3);
   };
@@ -217,14 +228,11 @@ void CalibrationTool_SavePlanePoints(const std::vector<Oberserve> obs, const Eig
 // reference src/LaseCamCalCeres.cpp:385-433: per-scan robust line fit (the step before the solve).
 // One scan per call, as the reference; the library's batched form is clc_problem_line_fit.
 void LineFittingCeres(const std::vector<Eigen::Vector3d> Points, Eigen::Vector2d& Line) {
-  std::vector<double> pts;
-  pts.reserve(3 * Points.size());
-  for (const Eigen::Vector3d& q : Points) { pts.push_back(q.x()); pts.push_back(q.y()); pts.push_back(q.z()); }
   double line[2] = {Line(0), Line(1)};  // :403 (start value; the reference's caller leaves it uninitialised)
-  if (clc_line_fit_points(pts.data(), (int64_t)Points.size(), line, /*max_num_iterations=*/10) != CLC_OK) {  // :425
-    std::cerr << "libclc_b200: " << clc_last_error() << std::endl;
-    return;
-  }
+  const double* pts = Points.empty() ? nullptr : reinterpret_cast<const double*>(Points.data());
+  static const double none[3] = {0.0, 0.0, 0.0};
+  if (clc_line_fit_points(pts ? pts : none, (int64_t)Points.size(), line, /*max_num_iterations=*/10) != CLC_OK)  // :425
+    fail("line fit");
   Line(0) = line[0];
   Line(1) = line[1];
 }

@@ -51,6 +51,23 @@ typedef struct {
   int device;                /* CUDA ordinal, -1 = current device */
 } clc_problem_desc;
 
+/* The same problem as the caller of the reference holds it: one separate array of Vector3d per frame -- Oberserve::points or
+ * ::points_on_line of every element of the std::vector<Oberserve> the reference's functions take BY VALUE
+ * (reference include/LaseCamCalCeres.h:22-23,28; Eigen::Vector3d is three contiguous doubles, so
+ * obs[f].points.data() is frame_points[f]).  The library gathers the frames itself (pack threads -> pinned ring -> PCIe
+ * -> layout kernel, all overlapped); pageable memory is fine.  replaces: the per-point loops of
+ * reference src/LaseCamCalCeres.cpp:233-254 (one heap CostFunction + LossFunction per point). */
+typedef struct {
+  int64_t n_frames;
+  const double* frame_pose;          /* host [n_frames*7] */
+  const double* const* frame_points; /* host [n_frames]: AoS xyz of frame f, frame_counts[f] points */
+  const int64_t* frame_counts;       /* host [n_frames] */
+  const double* edge_points;         /* host [n_frames*6] or NULL */
+  int use_loss;
+  double cauchy_a;
+  int device;                        /* ignored by the clc_group_* entry points (they take a device list) */
+} clc_gather_desc;
+
 /* replaces: GenerateSimData(), reference main/calibr_simulation.cpp:10-108, scaled to n_frames x beams and run
  * on the device (the 48 GB of BASELINE config 4 cannot pass through std::vector<Oberserve>). */
 typedef struct {
@@ -139,6 +156,8 @@ void clc_lm_default_options(clc_lm_options* opt);
 /* Uploads (H2D) and lays the problem out in HBM (SoA points, per-frame planes).  replaces: problem assembly,
  * reference src/LaseCamCalCeres.cpp:222-295 (no per-residual heap objects are created). */
 int clc_problem_create(clc_problem** out, const clc_problem_desc* desc);
+/* Same from per-frame arrays (the marshalled form of std::vector<Oberserve> without flattening it on the host). */
+int clc_problem_create_gather(clc_problem** out, const clc_gather_desc* desc);
 /* Same, generated on the device. */
 int clc_problem_create_synthetic(clc_problem** out, const clc_synthetic_desc* desc);
 int clc_problem_destroy(clc_problem* p);
@@ -233,6 +252,31 @@ int clc_comm_p2p_import(clc_comm* comm, const void* handles /* [nranks*64] */);
  * 1 = fused in-kernel peer exchange (needs clc_comm_p2p_import; the default once it has been called) */
 int clc_problem_set_allreduce_mode(clc_problem* p, int mode);
 
+/* ---- in-process multi-GPU: ONE process (one host thread) drives G devices ---------------------------------------
+ * What lets the unmodified reference callers (main/calibr_simulation.cpp:130, main/calibr_offline.cpp:170 -- one call of
+ * CamLaserCalibration() from one process) use every GPU of the box: the frames are sharded over the devices by point
+ * count (clc_shard_range), every device holds its shard for the whole solve, and the last block of every sweep kernel
+ * exchanges the 28 sums with plain peer stores (cudaDeviceEnablePeerAccess; the same sequence-tagged mailbox protocol as
+ * the multi-process path, no IPC handles, no NCCL).  All devices run the identical LM update.  A group of one device is
+ * a plain problem.  devices[i] = CUDA ordinal (-1 = current); an ordinal may appear only once. */
+typedef struct clc_group clc_group;
+int clc_group_create_gather(clc_group** out, const clc_gather_desc* desc, const int* devices, int n_devices);
+/* desc->frame_begin..frame_end is the range the GROUP holds (split evenly over its devices); desc->device is ignored */
+int clc_group_create_synthetic(clc_group** out, const clc_synthetic_desc* desc, const int* devices, int n_devices);
+int clc_group_destroy(clc_group* g);
+int clc_group_size(const clc_group* g, int* n_devices, int64_t* n_frames, int64_t* n_points);
+int clc_group_problem(clc_group* g, int index, clc_problem** out); /* borrowed: shard `index` (tests, measurement) */
+/* the collective forms of clc_eval / clc_solve_lm / clc_information / clc_closed_form (same outputs) */
+int clc_group_eval(clc_group* g, const double pose7[7], double H36[36], double g6[6], double* cost);
+int clc_group_solve_lm(clc_group* g, double pose7[7], const clc_lm_options* opt, clc_lm_summary* summary,
+                       clc_lm_iteration* trace, int trace_cap);
+int clc_group_information(clc_group* g, const double pose7[7], double H36[36], double b6[6], double* chi,
+                          double singular_values6[6], double V36[36]);
+int clc_group_closed_form(clc_group* g, double Tlc16[16], int* unobservable, double AtA81[81], double Atb9[9]);
+/* The device list the reference-facing drop-in uses (its signatures have no device argument): environment variable
+ * CLC_DEVICES = "0,1,2,3" | "all" | unset (the current device only).  Writes at most `cap` ordinals. */
+int clc_default_devices(int* devices, int cap, int* n);
+
 /* ---- measurement hooks (bench.py) ---------------------------------------------------------------------- */
 /* Launches K1 `n` times at pose7 on the problem's stream; each launch is bracketed by its own CUDA events.
  * flush_l2 != 0 overwrites a buffer larger than L2 between launches (outside the timed brackets).
@@ -251,6 +295,19 @@ int clc_problem_streamed_bytes(const clc_problem* p, int64_t* bytes);
  * every warp of the grid a 256-point stage (about 6*10^5 points on a B200) are latency-bound and stay on the general
  * kernels in either mode (environment override for tests: CLC_PLANAR_MIN_POINTS). */
 int clc_problem_set_planar_mode(clc_problem* p, int mode);
+/* Statistics of this process's most recent host -> HBM point upload: wall time of the pipeline, time the issuing thread
+ * waited for the pack threads, bytes that crossed PCIe (16 per point while every z is 0, else 24), chunks, pack threads,
+ * direct = 1 when the caller's buffer was pinned and used as the DMA source.  Any pointer may be NULL. */
+int clc_upload_last_stats(double* total_ms, double* pack_wait_ms, int64_t* bytes_h2d, int* chunks, int* pack_threads,
+                          int* direct);
+/* Test hook, no CUDA: what the pack threads write for the local point range [a, b) of a gathered problem -- packed x,y
+ * pairs (xy != 0; *nonplanar = a z != 0 or NaN was met) or packed x,y,z. */
+int clc_debug_pack(int64_t n_frames, const double* const* frame_points, const int64_t* frame_counts, int64_t a, int64_t b,
+                   int xy, double* out, int* nonplanar);
+/* Raw PCIe yardstick: `reps` host(pinned) -> device copies of `bytes` on `device`, each timed with CUDA events. */
+int clc_bench_h2d(int64_t bytes, int device, int reps, float* ms_each);
+/* Bytes clc_solve_lm reads back per solve (LM state + iteration trace). */
+int64_t clc_solve_readback_bytes(void);
 /* Pinned host memory for upload buffers. */
 int clc_host_alloc(void** ptr, int64_t bytes);
 int clc_host_free(void* ptr);

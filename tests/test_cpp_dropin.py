@@ -15,13 +15,27 @@ def build_driver(out_dir):
 
     _lib.load()
     exe = os.path.join(out_dir, "host_dropin_test")
-    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    pkg = os.path.join(ROOT, "camlasercalibratool_b200")
-    subprocess.check_call([cxx, "-O2", "-std=c++11", "-Wall", "-I", os.path.join(ROOT, "tests", "stubs"), "-I",
-                           os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "host_dropin_test.cpp"),
-                           os.path.join(pkg, "host", "LaseCamCalB200.cpp"), "-L", pkg, "-lclc_b200",
-                           "-Wl,-rpath," + pkg, "-o", exe])
+    # against the reference's own include/LaseCamCalCeres.h when /root/reference exists (build container), else the stand-in
+    subprocess.check_call(_build.cxx_command([os.path.join(ROOT, "tests", "host_dropin_test.cpp"), _build.DROPIN_SRC], exe))
     return exe
+
+
+def test_dropin_compiles_against_the_reference_header_when_present():
+    from camlasercalibratool_b200 import _build
+
+    dirs = _build.interface_include_dirs()
+    if os.path.exists("/root/reference/include/LaseCamCalCeres.h"):
+        assert dirs[0] == "/root/reference/include"  # the genuine interface wins over tests/stubs/LaseCamCalCeres.h
+    else:
+        assert dirs[0].endswith(os.path.join("tests", "stubs"))
+
+
+def test_bench_driver_builds():
+    from camlasercalibratool_b200 import _build
+
+    exe = _build.build_dropin_bench(force=True)
+    out = subprocess.check_output(["nm", "-C", "--defined-only", exe], text=True)
+    assert "CamLaserCalibration(" in out
 
 
 def test_dropin_compiles_and_links(tmp_path):
