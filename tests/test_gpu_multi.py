@@ -68,13 +68,14 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
-def test_two_gpu_solve_matches_single_gpu(oracle, tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_process_solve_matches_single_gpu(oracle, tmp_path, world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
     from camlasercalibratool_b200 import Problem
 
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     r = [np.load(tmp_path / f"rank{k}.npz") for k in range(world)]
     for k in range(1, world):  # every rank holds the identical all-reduced result and took the same decisions
