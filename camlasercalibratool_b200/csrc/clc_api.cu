@@ -689,11 +689,17 @@ int validate_offsets(int64_t N, const int64_t* offsets) {
 
 // uploads and finishes a set of freshly created shells; destroys all of them on failure
 int upload_and_finish(std::vector<clc_problem*>& problems, std::vector<UploadShard>& shards) {
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = upload_points(shards);
+  const auto t1 = std::chrono::steady_clock::now();
   for (size_t g = 0; g < problems.size() && rc == CLC_OK; ++g) {
     cudaSetDevice(problems[g]->device);
     rc = finish_create(problems[g]);
   }
+  if (std::getenv("CLC_UPLOAD_TIMING"))
+    std::fprintf(stderr, "CLC_UPLOAD_TIMING upload_points_ms=%.3f finish_create_ms=%.3f\n",
+                 std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   if (rc != CLC_OK) {
     const std::string msg = g_last_error;
     for (clc_problem* p : problems) clc_problem_destroy(p);
@@ -1782,11 +1788,22 @@ int clc_bench_eval(clc_problem* p, const double pose7[7], int n, int flush_l2, f
   std::vector<cudaEvent_t> ev(2 * (size_t)n);
   for (auto& e : ev) CLC_CUDA(cudaEventCreate(&e));
   const bool loss = p->use_loss != 0, edges = p->n_edges > 0;
+  // The flush kernels run with the sweep kernel's shared-memory carve-out (CLC_FLUSH_SMEM=0 disables): an SM that has to
+  // switch its L1/shared split between two kernels drains first, and in the LM loop the sweeps follow each other with
+  // the same split -- the timed launch should not pay a reconfiguration the product never sees.
+  int flush_smem = clc::dyn_smem_bytes(p->planar);
+  if (const char* env = std::getenv("CLC_FLUSH_SMEM")) {
+    if (std::atoi(env) == 0) flush_smem = 0;
+  }
+  if (flush_l2 && flush_smem > 0) {
+    CLC_CUDA(cudaFuncSetAttribute(clc::clc_flush_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, flush_smem));
+    CLC_CUDA(cudaFuncSetAttribute(clc::clc_flush_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, flush_smem));
+  }
   for (int i = 0; i < n; ++i) {
     if (flush_l2) {
-      clc::clc_flush_kernel<<<p->num_sms * 4, 256, 0, p->stream>>>(p->flush_buf, p->flush_n, (double)i);
+      clc::clc_flush_kernel<<<p->num_sms, 1024, flush_smem, p->stream>>>(p->flush_buf, p->flush_n, (double)i);
       CLC_LAUNCH_CHECK();
-      clc::clc_flush_read_kernel<<<p->num_sms * 4, 256, 0, p->stream>>>(p->flush_buf, p->flush_n, p->flush_buf);
+      clc::clc_flush_read_kernel<<<p->num_sms, 1024, flush_smem, p->stream>>>(p->flush_buf, p->flush_n, p->flush_buf);
       CLC_LAUNCH_CHECK();
     }
     CLC_CUDA(cudaEventRecord(ev[2 * i], p->stream));

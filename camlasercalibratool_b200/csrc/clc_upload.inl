@@ -151,31 +151,32 @@ inline void for_each_run(const UploadShard& s, int64_t a, int64_t b, F&& fn) {
   }
 }
 
+// inner loops with non-temporal stores: clc_pack.cpp
+extern "C" uint64_t clc_pack_xy_run(const double* src, int64_t n, double* dst);
+extern "C" void clc_pack_xyz_run(const double* src, int64_t n, double* dst);
+extern "C" void clc_pack_fence(void);
+
 void pack_xyz(const UploadShard& s, int64_t a, int64_t b, double* dst) {
   for_each_run(s, a, b, [&](const double* src, int64_t n) {
-    std::memcpy(dst, src, sizeof(double) * 3 * (size_t)n);
+    clc_pack_xyz_run(src, n, dst);
     dst += 3 * n;
   });
+  clc_pack_fence();
 }
 
 // packs x,y only; returns true when some z is not exactly zero (-0.0 counts as zero, NaN does not)
 bool pack_xy(const UploadShard& s, int64_t a, int64_t b, double* dst) {
   uint64_t any = 0;
   for_each_run(s, a, b, [&](const double* src, int64_t n) {
-    for (int64_t i = 0; i < n; ++i) {
-      dst[2 * i] = src[3 * i];
-      dst[2 * i + 1] = src[3 * i + 1];
-      uint64_t zb;
-      std::memcpy(&zb, src + 3 * i + 2, sizeof(zb));
-      any |= zb << 1;
-    }
+    any |= clc_pack_xy_run(src, n, dst);
     dst += 2 * n;
   });
+  clc_pack_fence();
   return any != 0;
 }
 
 struct UploadStats {  // filled for clc_upload_last_stats (measurement hook)
-  double pack_wait_ms = 0.0, total_ms = 0.0;
+  double pack_wait_ms = 0.0, total_ms = 0.0, setup_ms = 0.0, issue_ms = 0.0, drain_ms = 0.0;
   int64_t bytes_h2d = 0;
   int chunks = 0, repacked = 0, threads = 0, direct = 0;
 };
@@ -300,6 +301,7 @@ int upload_points(std::vector<UploadShard>& shards) {
   }
 
   // ---- issue loop (this thread) ----
+  const auto t_setup = std::chrono::steady_clock::now();
   std::vector<cudaEvent_t> ev_copied(n_chunks, nullptr);
   int status = CLC_OK;
   int completed = 0, next_issue = 0;
@@ -368,6 +370,7 @@ int upload_points(std::vector<UploadShard>& shards) {
     ++s.issued;
     ++next_issue;
   }
+  const auto t_issued = std::chrono::steady_clock::now();
   if (status != CLC_OK) abort_flag.store(true);
   allowed.store(n_chunks + K);  // let the packers run out (they only touch slots nobody reads any more on failure)
   if (!direct) {
@@ -405,7 +408,15 @@ int upload_points(std::vector<UploadShard>& shards) {
   g_last_upload.repacked = repacked;
   g_last_upload.threads = direct ? 0 : parts;
   g_last_upload.direct = direct ? 1 : 0;
-  g_last_upload.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  const auto t_end = std::chrono::steady_clock::now();
+  g_last_upload.total_ms = std::chrono::duration<double, std::milli>(t_end - t_begin).count();
+  g_last_upload.setup_ms = std::chrono::duration<double, std::milli>(t_setup - t_begin).count();
+  g_last_upload.issue_ms = std::chrono::duration<double, std::milli>(t_issued - t_setup).count();
+  g_last_upload.drain_ms = std::chrono::duration<double, std::milli>(t_end - t_issued).count();
+  if (std::getenv("CLC_UPLOAD_TIMING"))
+    std::fprintf(stderr, "CLC_UPLOAD_TIMING setup_ms=%.3f issue_ms=%.3f (pack_wait_ms=%.3f) drain_ms=%.3f chunks=%d threads=%d MB=%.1f\n",
+                 g_last_upload.setup_ms, g_last_upload.issue_ms, pack_wait_ms, g_last_upload.drain_ms, n_chunks, g_last_upload.threads,
+                 bytes_h2d / 1e6);
   return status;
 }
 

@@ -15,8 +15,10 @@
 // process -- frames sharded by point count, 28 sums exchanged over NVLink inside the sweep kernel.
 #include "LaseCamCalCeres.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -91,6 +93,25 @@ clc_group* create(const Marshalled& m) {
   return g;
 }
 
+// CLC_DROPIN_TIMING=1: phase times of CamLaserCalibration() on stderr (what bench.py's end-to-end breakdown reads)
+struct PhaseClock {
+  bool on;
+  std::chrono::steady_clock::time_point t;
+  std::string line;
+  PhaseClock() : on(std::getenv("CLC_DROPIN_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+  void lap(const char* name) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), " %s=%.3f", name, std::chrono::duration<double, std::milli>(now - t).count());
+    line += buf;
+    t = now;
+  }
+  ~PhaseClock() {
+    if (on) std::fprintf(stderr, "CLC_DROPIN_TIMING%s\n", line.c_str());
+  }
+};
+
 void print4(const double T[16]) {
   for (int r = 0; r < 4; ++r) std::cout << T[r * 4] << " " << T[r * 4 + 1] << " " << T[r * 4 + 2] << " " << T[r * 4 + 3] << "\n";
 }
@@ -136,9 +157,12 @@ void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl,
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 4; ++c) T[r * 4 + c] = Tcl(r, c);
   clc_T_to_pose7(T, pose);  // :215-219 (Eigen::Quaterniond(Matrix3d) restated in the library)
+  PhaseClock clock;
   Marshalled m;
   marshal(obs, use_linefitting_data, use_boundary_constraint, &m);
+  clock.lap("marshal_ms");
   clc_group* p = create(m);
+  clock.lap("upload_ms");
 
   clc_lm_options opt;
   clc_lm_default_options(&opt);  // DENSE_QR-equivalent step, max_num_iterations = 100 (:303-304), Ceres defaults
@@ -151,6 +175,7 @@ void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl,
   if (sum.termination == CLC_TERM_FAILURE) {  // Ceres would report FAILURE and leave the parameters at the start value
     std::cout << "Termination: FAILURE (no usable step / non-finite evaluation); Tcl left unchanged" << std::endl;
   }
+  clock.lap("solve_ms");
   // the counterpart of summary.FullReport() (:309)
   std::cout << "\nSolver Summary (libclc_b200, on-device Levenberg-Marquardt)\n";
   std::cout << "iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius\n";
@@ -169,6 +194,7 @@ void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl,
     for (int c = 0; c < 4; ++c) Tcl(r, c) = T[r * 4 + c];  // :311-314 (bottom row untouched)
 
   // ---- analysis tail (:316-381) ----
+  clock.lap("report_ms");
   double H[36], b[6], chi = 0.0, sv[6], V[36];
   if (clc_group_information(p, pose, H, b, &chi, sv, V) == CLC_OK) {
     std::cout << "----- H singular values--------:\n";
@@ -189,7 +215,9 @@ void CamLaserCalibration(const std::vector<Oberserve> obs, Eigen::Matrix4d& Tcl,
     clc_group_destroy(p);
     fail("information matrix");
   }
+  clock.lap("information_ms");
   clc_group_destroy(p);
+  clock.lap("destroy_ms");
 }
 
 // reference src/LaseCamCalCeres.cpp:68-110 (pure host I/O; kept so that the translation unit stays a complete

@@ -159,6 +159,23 @@ int main(int argc, char** argv) {
     raw_h2d_ms = median(v);
   }
 
+  // ---- what the by-value signature costs the CALLER, with nothing of ours involved: deep copy and destruction ----
+  double copy_ms = 0.0, destroy_ms = 0.0;
+  {
+    std::vector<double> c, d;
+    for (int it = 0; it < 3; ++it) {
+      const double t0 = now_ms();
+      std::vector<Oberserve>* tmp = new std::vector<Oberserve>(obs);
+      const double t1 = now_ms();
+      delete tmp;
+      const double t2 = now_ms();
+      c.push_back(t1 - t0);
+      d.push_back(t2 - t1);
+    }
+    copy_ms = median(c);
+    destroy_ms = median(d);
+  }
+
   // ---- timed calls ----
   std::vector<double> ms_moved, ms_lvalue;
   double max_dev = 0.0;
@@ -198,10 +215,10 @@ int main(int argc, char** argv) {
       "\"ms_per_call_lvalue_median\": %.6f, \"sweeps_per_call\": %d, \"lm_iterations\": %d, \"termination\": %d, "
       "\"lm_device_ms\": %.6f, \"h2d_bytes_per_call\": %lld, \"d2h_bytes_per_call\": %d, \"raw_h2d_ms_same_bytes\": %.6f, "
       "\"upload_ms\": %.6f, \"upload_pack_wait_ms\": %.6f, \"upload_chunks\": %d, \"pack_threads\": %d, \"upload_direct\": %d, "
-      "\"max_abs_dev_vs_c_abi_solve\": %.3e}\n",
+      "\"caller_copy_of_obs_ms\": %.6f, \"caller_destruction_of_obs_ms\": %.6f, \"max_abs_dev_vs_c_abi_solve\": %.3e}\n",
       (long long)frames, (long long)beams, (long long)n_points, edges, n_devices, steps, warmup, mean_moved, median(ms_moved),
       *std::min_element(ms_moved.begin(), ms_moved.end()), *std::max_element(ms_moved.begin(), ms_moved.end()),
       median(ms_lvalue), sweeps_per_call, lm_iterations, termination, lm_device_ms, (long long)h2d_bytes,
-      (int)clc_solve_readback_bytes() + 28 * 8, raw_h2d_ms, upload_ms, upload_pack_wait_ms, upload_chunks, pack_threads, upload_direct, max_dev);
+      (int)clc_solve_readback_bytes() + 28 * 8, raw_h2d_ms, upload_ms, upload_pack_wait_ms, upload_chunks, pack_threads, upload_direct, copy_ms, destroy_ms, max_dev);
   return max_dev < 1e-9 ? 0 : 3;
 }

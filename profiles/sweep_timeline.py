@@ -19,18 +19,19 @@ with Problem.synthetic(frames, beams, seed=7, sigma=0.01) as p:
     p.bench_eval(x, 5, True)
     for with_lm in (0, 1):
         for flush in (1, 0):
-            rows = []
+            rows, keep = [], []
             for rep in range(5):
                 buf = (C.c_ulonglong * (8 * 4096))()
                 grid = C.c_int()
                 _lib.check(L.clc_debug_sweep_timing(p._h, x.ctypes.data_as(_lib.c_double_p), with_lm, flush, buf, C.byref(grid)), "timing")
                 t = np.array(buf[: 8 * grid.value], dtype=np.float64).reshape(grid.value, 8)
                 t0 = t[:, 0].min()
+                keep.append(t.copy())
                 last = int(np.argmax(t[:, 4]))
                 rows.append([t[:, 0].max() - t0, np.median(t[:, 1]) - t0, t[:, 1].max() - t0, t[:, 2].max() - t0, t[:, 3].max() - t0,
                              t[last, 4] - t0, t[last, 5] - t0])
             if with_lm == 0 and flush == 1:
-                np.save(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "timeline_blocks.npy"), t)
+                np.save(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out", "timeline_blocks.npy"), np.array(keep))
             r = np.median(np.array(rows), axis=0) / 1e3
             print(f"lm={with_lm} flush_l2={flush} grid={grid.value}: last block start {r[0]:6.2f} | stream done median {r[1]:6.2f} max {r[2]:6.2f} | "
                   f"tiles flushed {r[3]:6.2f} | partials written {r[4]:6.2f} | final sums {r[5]:6.2f} | after LM {r[6]:6.2f}  (us since first block start)")
