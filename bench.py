@@ -56,7 +56,9 @@ def parse_args():
     ap.add_argument("--kernel-launches", type=int, default=100, help="timed launches of the sweep kernel for the roofline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: ncclAllReduce between kernels instead of the fused peer exchange")
-    ap.add_argument("--no-config3", action="store_true", help="skip the supplementary 4.8 GB (configs[2]) measurement")
+    ap.add_argument("--no-config3", action="store_true", help="skip the supplementary 4.8 GB rows (configs[2] and configs[4])")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (configs[3], 48 GB over the N ranks)")
+    ap.add_argument("--strong-frames", type=int, default=1_000_000)
     return ap.parse_args()
 
 
@@ -178,6 +180,12 @@ def cpu_baseline(frames, beams, quick=False):
     return out
 
 
+def workload_config(args, world):
+    """The `config` both arms print (the reference arm runs a bounded sample of it; see its cpu_baseline.sample)."""
+    return {"workload": f"BASELINE configs[1]: {args.frames} frames x {args.beams} points per GPU, calibr_simulation generator "
+                        f"(exact-M), sigma={SIGMA} m, identity start, full LM solve to Ceres convergence"}
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -208,8 +216,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / steps_done, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: {args.frames} frames x {args.beams} points per GPU, sigma={SIGMA} m, "
-                               f"identity start, full LM solve (bounded CPU sample: {n} frames)"},
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference itself (Ceres+Eigen+ROS) cannot be built in this image; this is the CPU oracle port",
@@ -218,19 +225,87 @@ def run_reference(args):
 
 
 # ---- our arm ----------------------------------------------------------------------------------------------------------
+GT_TLC = np.array([[0.0, 0.0, 1.0, 0.1], [-1.0, 0.0, 0.0, 0.2], [0.0, -1.0, 0.0, 0.3], [0.0, 0.0, 0.0, 1.0]])  # calibr_simulation.cpp:15-20
+
+
+def pose_error_vs_ground_truth(x):
+    """(rotation angle [rad], translation distance [m]) between pose7 x (T_cl) and the generator's ground truth."""
+    from camlasercalibratool_b200.api import pose7_to_T
+
+    T = np.asarray(pose7_to_T(x)).reshape(4, 4)
+    Tgt = np.linalg.inv(GT_TLC)
+    dR = T[:3, :3].T @ Tgt[:3, :3]
+    ang = float(np.arccos(np.clip((np.trace(dR) - 1.0) / 2.0, -1.0, 1.0)))
+    return ang, float(np.linalg.norm(T[:3, 3] - Tgt[:3, 3]))
+
+
+def run_dropin(frames, beams, steps, warmup, devices=None, edges=0, sigma=SIGMA, seed=SEED, timeout=900):
+    """Runs the C++ end-to-end driver (host/dropin_bench.cpp: std::vector<Oberserve> -> CamLaserCalibration() of the drop-in)
+    as a child process and returns its JSON."""
+    from camlasercalibratool_b200 import _build
+
+    exe = _build.BENCH_EXE
+    if not os.path.exists(exe):
+        exe = _build.build_dropin_bench()
+    env = dict(os.environ)
+    if devices is not None:
+        env["CLC_DEVICES"] = ",".join(str(d) for d in devices)
+    cmd = [exe, str(frames), str(beams), repr(sigma), str(seed), str(steps), str(warmup), str(edges)]
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=timeout)
+    for line in res.stdout.splitlines():
+        if line.startswith("CLC_DROPIN_JSON "):
+            out = json.loads(line[len("CLC_DROPIN_JSON "):])
+            out["rc"] = res.returncode
+            return out
+    raise RuntimeError(f"clc_dropin_bench failed (rc {res.returncode}): {res.stderr[-400:]}")
+
+
+def kernel_row(prob, x, n_launch, peaks, label):
+    """Roofline row of the sweep kernel on `prob` as configured: per-launch CUDA events, L2 flushed between launches."""
+    prob.bench_eval(x, 5, flush_l2=True)
+    ms = prob.bench_eval(x, n_launch, flush_l2=True)
+    mean = float(np.mean(ms))
+    nbytes = prob.streamed_bytes()
+    n_points = prob.sizes()[1]
+    ach = nbytes / (mean * 1e-3) / 1e9
+    return {"kernel": label, "bound": "hbm", "achieved": ach, "peak": peaks, "unit": "GB/s", "frac": ach / peaks,
+            "kernel_ms_mean": mean, "kernel_ms_min": float(np.min(ms)), "kernel_ms_median": float(np.median(ms)),
+            "algorithmic_bytes_per_launch": nbytes, "residuals_per_s_kernel": n_points / (mean * 1e-3), "launches_timed": n_launch}
+
+
+def solve_row(prob, opt, reps, n_points_total, max_over_ranks, barrier):
+    """K full LM solves; returns throughput figures (device time, max over ranks)."""
+    prob.solve(X0, opt)
+    barrier()
+    ms, sweeps, iters, per = 0.0, 0, 0, []
+    x = X0
+    for _ in range(reps):
+        x, s, _ = prob.solve(X0, opt)
+        ms += s.device_ms
+        per.append(s.device_ms)
+        sweeps += s.num_sweeps
+        iters += s.num_iterations - 1
+    barrier()
+    ms = max_over_ranks(ms)
+    return x, {"ms_per_solve": ms / reps, "sweeps_per_solve": sweeps / reps, "lm_iterations_per_solve": iters / reps,
+               "residual_evals_per_s": n_points_total * sweeps / (ms * 1e-3), "lm_iters_per_s": iters / (ms * 1e-3),
+               "termination": int(s.termination)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from camlasercalibratool_b200 import Comm, Problem, comm_unique_id, default_options, launch_count
-    from camlasercalibratool_b200.api import pinned_array
 
     rank, local_rank, world = dist_env()
     if args.gpus != world:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")  # host-only rendezvous: does not put a spinning kernel on the GPUs
 
     def barrier():
         if world > 1:
@@ -244,12 +319,26 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def sum_over_ranks(v):
+    def sum_over_ranks(a):
+        a = np.atleast_1d(np.asarray(a, dtype=np.float64))
         if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+            return a
+        t = torch.tensor(a, dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return t.cpu().numpy()
+
+    peaks, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy burst)"
+    except Exception:
+        pass
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
 
     frames_total = args.frames * world
     f0, f1 = rank * args.frames, (rank + 1) * args.frames
@@ -257,7 +346,7 @@ def run_ours(args):
     n_frames, n_points, _ = prob.sizes()
     # The simulated laser is two-dimensional, so the library would drop the z stream (16 B per residual).  SURVEY.md 8(d)
     # fixes the contract figure at 24 B per residual: the headline legs run the general three-stream kernels; the planar
-    # kernels are reported as their own row ("planar") with their own byte count.
+    # kernels are reported as their own row (roofline.planar) with their own byte count.
     prob.set_planar_mode(0)
     comm = None
     if world > 1:
@@ -270,13 +359,11 @@ def run_ours(args):
             dist.all_gather_object(out, blob)
             return out
 
-        p2p_note = "fused into the sweep kernel (NVLink peer stores, sequence-tagged words, rank-order sum)"
         if not args.nccl_allreduce:
             try:
                 comm.enable_p2p(all_gather)  # fused in-kernel all-reduce over NVLink peer memory
-            except Exception as exc:  # no peer access between these GPUs: the NCCL path still works
+            except Exception:  # no peer access between these GPUs: the NCCL path still works
                 args.nccl_allreduce = True
-                p2p_note = f"peer exchange unavailable ({exc}); "
             ok = torch.tensor([0 if args.nccl_allreduce else 1], device="cuda")
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks must use the same mode
             if int(ok.item()) == 0 and not args.nccl_allreduce:
@@ -286,7 +373,12 @@ def run_ours(args):
                 dist.broadcast_object_list(uid, src=0)
                 comm = Comm(uid[0], world, rank, device=local_rank)
         prob.attach_comm(comm)
+        # the first collective sweeps after the peer mappings were created are slow (lazy peer-access set-up, cold mailboxes):
+        # run them outside every timed region
+        for _ in range(20):
+            prob.eval(X0)
     opt = default_options()
+    total_points = float(sum_over_ranks(float(n_points))[0])
 
     # ---- resident-data leg: K full solves ----
     for _ in range(args.warmup):
@@ -297,11 +389,12 @@ def run_ours(args):
     launches0 = launch_count()
     barrier()
     t0 = time.perf_counter()
-    dev_ms, sweeps, iters = 0.0, 0, 0
+    dev_ms, sweeps, iters, per_step = 0.0, 0, 0, []
     x = X0
     for _ in range(args.steps):
         x, s, _ = prob.solve(X0, opt)
         dev_ms += s.device_ms
+        per_step.append(s.device_ms)
         sweeps += s.num_sweeps
         iters += s.num_iterations - 1
     barrier()
@@ -309,201 +402,152 @@ def run_ours(args):
     launches = launch_count() - launches0
     dev_ms = max_over_ranks(dev_ms)
     wall_ms = max_over_ranks(wall_ms)
-    total_points = sum_over_ranks(float(n_points))
     value = total_points * sweeps / (dev_ms * 1e-3)
     lm_iters_per_s = iters / (dev_ms * 1e-3)
+    step_stats = {"min": float(np.min(per_step)), "median": float(np.median(per_step)), "max": float(np.max(per_step)),
+                  "first": float(per_step[0]), "what": "device ms per solve on rank 0"}
+
+    # ---- check block (outside every timed region): the answer, at this N ----
+    check = {}
+    cost_c, H_c, g_c = prob.eval(x)  # collective (fused exchange when world > 1)
+    if world > 1:
+        prob.attach_comm(None)
+        cost_l, H_l, g_l = prob.eval(x)  # this shard alone
+        prob.attach_comm(comm)
+        tot = sum_over_ranks(np.concatenate([[cost_l], H_l.ravel(), g_l]))
+        ref = np.concatenate([[cost_c], H_c.ravel(), g_c])
+        scale = max(np.abs(H_c).max(), abs(cost_c))
+        check["collective_vs_sum_of_shards_rel"] = float(np.abs(tot - ref).max() / scale)
+        check["collective_ok"] = bool(check["collective_vs_sum_of_shards_rel"] <= 1e-11)
+    with Problem.synthetic(frames_total, args.beams, seed=SEED, sigma=0.0, frame_begin=f0, frame_end=f1, device=local_rank) as clean:
+        clean.set_planar_mode(0)
+        clean.attach_comm(comm)
+        xc, sc, _ = clean.solve(X0, opt)
+        ang, dt = pose_error_vs_ground_truth(xc)
+        check.update({"noise_free_rot_err_rad": ang, "noise_free_trans_err_m": dt, "noise_free_ok": bool(ang < 1e-9 and dt < 1e-9),
+                      "noise_free_iterations": int(sc.num_iterations - 1)})
+        clean.attach_comm(None)
+    ang_n, dt_n = pose_error_vs_ground_truth(x)
+    check.update({"noisy_rot_err_rad": ang_n, "noisy_trans_err_m": dt_n})
 
     # ---- roofline leg: the sweep kernel alone, L2 flushed between launches (local shard, no collective) ----
-    prob.bench_eval(x, 5, flush_l2=True)
-    k_ms = prob.bench_eval(x, args.kernel_launches, flush_l2=True)
-    launches += args.kernel_launches
+    roofline = kernel_row(prob, x, args.kernel_launches, peaks, "clc_sweep_kernel<LOSS,LM> general, 24 B/residual")
     k_b2b = prob.bench_eval(x, args.kernel_launches, flush_l2=False)
-    launches += args.kernel_launches
-    k_mean = float(np.mean(k_ms))
-    alg_bytes = prob.algorithmic_bytes()
-    peaks, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy burst)"
-    except Exception:
-        pass
-    achieved = alg_bytes / (k_mean * 1e-3) / 1e9
-    traffic = traffic_planar = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tj = json.load(f)
-            traffic = tj.get("dram_bytes_per_launch")
-            traffic_planar = (tj.get("planar") or {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks, "unit": "GB/s", "frac": achieved / peaks,
-                "traffic": traffic, "kernel": "clc_sweep_kernel<LOSS,LM>", "kernel_ms_mean": k_mean,
-                "kernel_ms_min": float(np.min(k_ms)), "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "residuals_per_s_kernel": n_points / (k_mean * 1e-3),
-                "back_to_back_no_flush": {"kernel_ms_mean": float(np.mean(k_b2b)), "achieved": alg_bytes / (float(np.mean(k_b2b)) * 1e-3) / 1e9,
-                                          "frac": alg_bytes / (float(np.mean(k_b2b)) * 1e-3) / 1e9 / peaks,
-                                          "note": "inputs (240 MB) exceed the 126 MB L2 but part of them survives between launches"},
-                "l2": "flushed between launches (256 MiB written, then read back so that no dirty lines are left)"}
+    roofline.update({"traffic": traffic.get("dram_bytes_per_launch"), "traffic_source": traffic.get("source"),
+                     "peak_source": peak_src,
+                     "l2": "flushed between launches (256 MiB written, then read back: no dirty lines left)",
+                     "back_to_back_no_flush_ms": float(np.mean(k_b2b))})
 
-    # ---- separate row: the planar (two-stream) kernels the library picks by itself for z == 0 data ----
-    planar = None
+    # ---- separate row: the planar (two-stream) kernels the library picks by itself for z == 0 data (16 B/residual) ----
     prob.set_planar_mode(1)
     if prob.planar:
-        lc0 = launch_count()
-        for _ in range(args.warmup):
-            prob.solve(X0, opt)
-        barrier()
-        p_ms, p_sweeps, p_iters = 0.0, 0, 0
-        for _ in range(args.steps):
-            _, s, _ = prob.solve(X0, opt)
-            p_ms += s.device_ms
-            p_sweeps += s.num_sweeps
-            p_iters += s.num_iterations - 1
-        barrier()
-        p_ms = max_over_ranks(p_ms)
-        prob.bench_eval(x, 5, flush_l2=True)
-        pk_ms = prob.bench_eval(x, args.kernel_launches, flush_l2=True)
-        launches += launch_count() - lc0
-        pk_mean = float(np.mean(pk_ms))
-        p_bytes = prob.streamed_bytes()
-        planar = {"what": "z == 0 for every point (a 2-D laser): z stream dropped from HBM, two-stream kernels, results "
-                          "equal to the general kernels up to summation order; 16 B per residual -- own denominators, never mixed with the 24 B row",
-                  "value": total_points * p_sweeps / (p_ms * 1e-3), "unit": UNIT, "ms_per_step": p_ms / args.steps,
-                  "lm_iters_per_s": p_iters / (p_ms * 1e-3),
-                  "roofline": {"bound": "hbm", "achieved": p_bytes / (pk_mean * 1e-3) / 1e9, "peak": peaks, "unit": "GB/s",
-                               "frac": p_bytes / (pk_mean * 1e-3) / 1e9 / peaks, "traffic": traffic_planar,
-                               "kernel": "clc_sweep_kernel<LOSS,LM,PLANAR>",
-                               "kernel_ms_mean": pk_mean, "kernel_ms_min": float(np.min(pk_ms)),
-                               "algorithmic_bytes_per_launch": p_bytes, "residuals_per_s_kernel": n_points / (pk_mean * 1e-3),
-                               "speedup_over_24B_kernel": k_mean / pk_mean}}
-
-    # ---- end-to-end leg: host (pinned) buffers -> create (H2D + layout) -> solve -> D2H result -> destroy ----
-    d = prob.download()
-    pin_pts = pinned_array(d["points"].shape)
-    pin_pts.array[...] = d["points"]
-    pin_fp = pinned_array(d["frame_pose"].shape)
-    pin_fp.array[...] = d["frame_pose"]
-    offsets = d["offsets"]
-    del d
-
-    def e2e_step():
-        with Problem.from_arrays(pin_fp.array, offsets, pin_pts.array, device=local_rank) as q:
-            q.attach_comm(comm)
-            _, ss, _ = q.solve(X0, opt)
-        return ss
-
-    e2e_steps = max(3, min(args.steps, 10))
-    e2e_sweeps = 0
-    e2e_step()  # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_sweeps += e2e_step().num_sweeps
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = total_points * e2e_sweeps / e2e_s
-    h2d = int(pin_pts.nbytes + pin_fp.nbytes + offsets.nbytes + 7 * 8 + 64)
-    d2h = int(7 * 8 + 64)
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": 1e3 * e2e_s / e2e_steps,
-           "what": "per rank: Problem.from_arrays(pinned host AoS, 24 B per point) [H2D + HBM layout + planarity detection] + "
-                   "clc_solve_lm (library default: planar kernels, the data have z == 0) + result read-back + destroy; wall "
-                   "clock, max over ranks; PCIe-bound: the 240 MB upload alone takes 4.3 ms at the measured 55 GB/s"}
-    pin_pts.free()
-    pin_fp.free()
+        row = kernel_row(prob, x, args.kernel_launches, peaks, "clc_sweep_kernel<LOSS,LM,PLANAR>, 16 B/residual (own denominator)")
+        row["traffic"] = (traffic.get("planar") or {}).get("dram_bytes_per_launch")
+        row["speedup_over_24B_kernel"] = roofline["kernel_ms_mean"] / row["kernel_ms_mean"]
+        _, srow = solve_row(prob, opt, args.steps, total_points, max_over_ranks, barrier)
+        row["full_lm_solve"] = srow
+        roofline["planar"] = row
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- supplementary: BASELINE configs[2] (10^5 frames x 2*10^3 points, 4.8 GB): the size BASELINE.json names for the
-    #      ncu capture of achieved HBM GB/s and for "full LM to convergence" ----
-    config3 = None
-    if world == 1 and not args.no_config3:
+    # ---- strong scaling: BASELINE configs[3] (10^6 frames x 2*10^3 points = 2*10^9 residuals, 48 GB) over the N ranks ----
+    strong = None
+    if not args.no_strong:
         prob.close()
+        prob = None
+        SF, SB = args.strong_frames, 2_000
+        sf0, sf1 = SF * rank // world, SF * (rank + 1) // world
+        with Problem.synthetic(SF, SB, seed=SEED, sigma=SIGMA, frame_begin=sf0, frame_end=sf1, device=local_rank) as big:
+            big.set_planar_mode(0)
+            big.attach_comm(comm)
+            xs, srow = solve_row(big, opt, 3, float(SF) * SB, max_over_ranks, barrier)
+            srow["gt_rot_err_rad"], srow["gt_trans_err_m"] = pose_error_vs_ground_truth(xs)
+            big.set_planar_mode(1)
+            _, prow = solve_row(big, opt, 3, float(SF) * SB, max_over_ranks, barrier)
+            big.attach_comm(None)
+        strong = {"workload": f"BASELINE configs[3]: {SF} frames x {SB} points, the SAME total problem at every N (frames sharded by rank)",
+                  "general_24B": srow, "planar_16B": prow}
+    elif prob is not None:
+        prob.close()
+        prob = None
+
+    # ---- end-to-end leg: std::vector<Oberserve> (pageable, one heap array per frame) -> CamLaserCalibration() of the C++
+    #      drop-in (the reference's own signature) on N devices of ONE process; rank 0 runs it, the others stay off the GPUs ----
+    e2e, config1 = None, None
+    if rank == 0:
+        e2e_steps = max(3, min(args.steps, 10))
+        dj = run_dropin(frames_total, args.beams, e2e_steps, 3, devices=list(range(world)))
+        pts = float(dj["points"])
+        e2e = {"value": pts * dj["sweeps_per_call"] / (dj["body_ms_mean"] * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(dj["h2d_bytes_per_call"]), "d2h_bytes_per_step": int(dj["d2h_bytes_per_call"]),
+               "ms_per_step": dj["body_ms_mean"], "ms_per_step_median": dj["body_ms_median"], "steps": e2e_steps,
+               "what": "C++ drop-in, pageable std::vector<Oberserve> input: CamLaserCalibration() entry to return",
+               "phases_ms": dj["phases_ms"], "raw_h2d_ms_same_bytes": dj["raw_h2d_ms_same_bytes"],
+               "upload_over_raw_h2d": dj["phases_ms"]["upload"] / max(dj["raw_h2d_ms_same_bytes"], 1e-9),
+               "sweeps_per_call": dj["sweeps_per_call"], "n_devices": dj["n_devices"], "pack_threads": dj["pack_threads"],
+               "call_expr_moved_ms": dj["call_expr_moved_ms_median"], "call_expr_lvalue_ms": dj["call_expr_lvalue_ms_median"],
+               "caller_copy_of_obs_ms": dj["caller_copy_of_obs_ms"], "caller_destruction_of_obs_ms": dj["caller_destruction_of_obs_ms"],
+               "by_value_note": "call_expr_* add what the reference's by-value signature makes the CALLER do (deep copy / destruction "
+                                "of the vector<Oberserve>); identical for the reference, none of it library code",
+               "max_abs_dev_vs_c_abi_solve": dj["max_abs_dev_vs_c_abi_solve"], "rc": dj["rc"]}
+        if world == 1:
+            c1 = run_dropin(50, 180, 20, 3, devices=[0], seed=1)
+            config1 = {"workload": "BASELINE configs[0]: 50 frames x 180 beams through the C++ drop-in",
+                       "body_ms": c1["body_ms_mean"], "call_expr_lvalue_ms": c1["call_expr_lvalue_ms_median"],
+                       "lm_device_ms": c1["lm_device_ms"], "lm_iterations": c1["lm_iterations"], "phases_ms": c1["phases_ms"]}
+            e2e["config1"] = config1
+    if world > 1:
+        dist.barrier(group=cpu_group)
+
+    # ---- supplementary rows (one GPU): BASELINE configs[2] and configs[4] ----
+    if world == 1 and not args.no_config3:
         with Problem.synthetic(100_000, 2_000, seed=SEED, sigma=SIGMA, device=local_rank) as big:
             big.set_planar_mode(0)  # contract row first (24 B per residual)
-            big.bench_eval(X0, 3, flush_l2=True)
-            ms3 = big.bench_eval(x, 20, flush_l2=True)
-            b3 = big.algorithmic_bytes()
-            for _ in range(2):
-                big.solve(X0, opt)
-            _, s3, _ = big.solve(X0, opt)
-            launches += 23 + 3 * s3.num_sweeps
+            r3 = kernel_row(big, x, 20, peaks, "general, 24 B/residual")
+            _, r3["full_lm_solve"] = solve_row(big, opt, 2, 2e8, max_over_ranks, barrier)
             big.set_planar_mode(1)
-            big.bench_eval(X0, 3, flush_l2=True)
-            ms3p = big.bench_eval(x, 20, flush_l2=True)
-            b3p = big.streamed_bytes()
-            big.solve(X0, opt)
-            _, s3p, _ = big.solve(X0, opt)
-            launches += 23 + 2 * s3p.num_sweeps
-            ach3 = b3 / (float(np.mean(ms3)) * 1e-3) / 1e9
-            config3 = {"workload": "BASELINE configs[2]: 100000 frames x 2000 points (4.8 GB), same generator",
-                       "roofline": {"bound": "hbm", "achieved": ach3, "peak": peaks, "unit": "GB/s", "frac": ach3 / peaks,
-                                    "kernel_ms_mean": float(np.mean(ms3)), "algorithmic_bytes_per_launch": b3,
-                                    "residuals_per_s_kernel": 2e8 / (float(np.mean(ms3)) * 1e-3)},
-                       "full_lm_solve": {"ms": s3.device_ms, "lm_iterations": s3.num_iterations - 1, "sweeps": s3.num_sweeps,
-                                         "residual_evals_per_s": 2e8 * s3.num_sweeps / (s3.device_ms * 1e-3),
-                                         "lm_iters_per_s": (s3.num_iterations - 1) / (s3.device_ms * 1e-3),
-                                         "termination": int(s3.termination)},
-                       "planar": {"kernel_ms_mean": float(np.mean(ms3p)), "algorithmic_bytes_per_launch": b3p,
-                                  "achieved": b3p / (float(np.mean(ms3p)) * 1e-3) / 1e9,
-                                  "frac": b3p / (float(np.mean(ms3p)) * 1e-3) / 1e9 / peaks,
-                                  "full_lm_solve_ms": s3p.device_ms, "sweeps": s3p.num_sweeps,
-                                  "residual_evals_per_s": 2e8 * s3p.num_sweeps / (s3p.device_ms * 1e-3)}}
-
-    # ---- supplementary: BASELINE configs[0], the reference's own problem size (50 frames x 180 beams), end to end through
-    #      the mirrored entry point (marshal + upload + on-device LM + analysis tail + destroy) next to the CPU oracle ----
-    config1 = None
-    if rank == 0 and world == 1:
-        from camlasercalibratool_b200 import CamLaserCalibration, Oberserve
-        from oracle import oracle as O
-
-        small = O.generate(50, 180, seed=1, sigma=0.01)
-        obs = [Oberserve(small.frame_pose[f, :4].copy(), small.frame_pose[f, 4:].copy(),
-                         small.points[small.offsets[f]:small.offsets[f + 1]], small.points[small.offsets[f]:small.offsets[f + 1]])
-               for f in range(small.n_frames)]
-        for _ in range(3):
-            CamLaserCalibration(obs, np.eye(4), False, verbose=False)
-        t0 = time.perf_counter()
-        reps = 20
-        for _ in range(reps):
-            rep = CamLaserCalibration(obs, np.eye(4), False, verbose=False)
-        gpu_ms = 1e3 * (time.perf_counter() - t0) / reps
-        launches += 23 * 20
-        t0 = time.perf_counter()
-        for _ in range(5):
-            O.solve(small, X0)
-        cpu_ms = 1e3 * (time.perf_counter() - t0) / 5
-        config1 = {"workload": "BASELINE configs[0]: 50 frames x 180 beams (5351 residuals), CamLaserCalibration() end to end",
-                   "gpu_ms_per_call": gpu_ms, "device_ms_of_the_lm": rep["device_ms"], "lm_iterations": rep["iterations"] - 1,
-                   "cpu_oracle_ms_per_solve_1_thread": cpu_ms}
+            r3p = kernel_row(big, x, 20, peaks, "planar, 16 B/residual")
+            _, r3p["full_lm_solve"] = solve_row(big, opt, 2, 2e8, max_over_ranks, barrier)
+            r3["planar"] = r3p
+            r3["workload"] = "BASELINE configs[2]: 100000 frames x 2000 points (4.8 GB)"
+            roofline["config3"] = r3
+        with Problem.synthetic(100_000, 2_000, seed=SEED, sigma=SIGMA, with_edges=True, camera="equi", pixel_sigma=0.3,
+                               device=local_rank) as c5:
+            c5.set_planar_mode(0)
+            r5 = kernel_row(c5, x, 20, peaks, "general + edge tail, 24 B/residual + 56 B/edge residual")
+            x5, r5["full_lm_solve"] = solve_row(c5, opt, 2, 2e8 + 2e5, max_over_ranks, barrier)
+            r5["gt_rot_err_rad"], r5["gt_trans_err_m"] = pose_error_vs_ground_truth(x5)
+            c5.set_planar_mode(1)
+            r5p = kernel_row(c5, x, 20, peaks, "planar + edge tail, 16 B/residual + 56 B/edge residual")
+            r5["planar"] = r5p
+            r5["workload"] = ("BASELINE configs[4]: 100000 frames x 2000 points + 200000 board-edge residuals, board poses from "
+                              "the equidistant (Kannala-Brandt) camera chain with 0.3 px corner noise")
+            roofline["config5"] = r5
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args.frames, args.beams)
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
+        cfg = workload_config(args, world)
+        cfg.update({"sharding": (f"frames by rank, {world} ranks, 28-double all-reduce per sweep: " +
+                                 ("ncclAllReduce between kernels" if args.nccl_allreduce else
+                                  "fused into the sweep kernel (NVLink peer stores, rank-order sum)")) if world > 1 else "single GPU",
+                    "l2": f"inputs ({roofline['algorithmic_bytes_per_launch'] / 1e6:.0f} MB/GPU) > 126 MB L2; roofline leg also flushes L2 between launches",
+                    "lm": "one fused residual+Jacobian+reduce sweep per LM iteration",
+                    "kernels": "general three-stream kernels (24 B/residual contract row); planar rows separate",
+                    "check": check, "strong_scaling": strong, "step_device_ms": step_stats})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[1]: {args.frames} frames x {args.beams} points per GPU "
-                                   f"({frames_total} frames total), calibr_simulation generator (exact-M), sigma={SIGMA} m, "
-                                   f"identity start, full LM solve to Ceres convergence",
-                       "sharding": (f"frames by rank, {world} rank(s), 28-double all-reduce per sweep: " +
-                                    ("ncclAllReduce between kernels" if args.nccl_allreduce else
-                                     "fused into the sweep kernel (NVLink peer stores, sequence-tagged words, rank-order sum)")) if world > 1 else "single GPU",
-                       "l2": f"inputs ({alg_bytes / 1e6:.0f} MB per GPU) larger than the 126 MB L2; roofline leg flushes L2 between launches",
-                       "lm": "one fused residual+Jacobian+reduce sweep per LM iteration (speculative Jacobian at the candidate)",
-                       "kernels": "general three-stream kernels (24 B per residual, the SURVEY.md 8(d) contract figure); the planar "
-                                  "two-stream kernels the library would pick for this z == 0 data are the separate row 'planar'"},
+            "dtype": "f64", "data": "synthetic", "config": cfg,
             "lm_iters_per_s": lm_iters_per_s, "sweeps_per_solve": sweeps / args.steps, "lm_iterations_per_solve": iters / args.steps,
-            "wall_ms_per_step": wall_ms / args.steps,
-            "roofline": roofline, "planar": planar, "config3": config3, "config1": config1, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "wall_ms_per_step": wall_ms / args.steps, "value_on_wall_clock": total_points * sweeps / (wall_ms * 1e-3),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches),
         }
         print(json.dumps(line))
-    prob.close()
     if comm is not None:
         comm.close()
     if world > 1:

@@ -246,10 +246,10 @@ struct clc_problem {
   int* warp_first_frame = nullptr;
   double* edge_plane = nullptr;
   double* edge_pt = nullptr;
-  double* partials = nullptr;
+  unsigned long long* partials_ll = nullptr;  // tagged block partials (clc_kernels.cuh)
+  unsigned int* launch_seq = nullptr;
   double* sums = nullptr;
   double* pose = nullptr;
-  unsigned int* ticket = nullptr;
   clc::LmState* lm = nullptr;
   double* flush_buf = nullptr;
   int64_t flush_n = 0;
@@ -309,9 +309,9 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
   clc::SweepArgs a;
   a.pose7 = d_pose;
   a.done = d_done;
-  a.partials = p->partials;
+  a.partials_ll = p->partials_ll;
   a.sums = p->sums;
-  a.ticket = p->ticket;
+  a.launch_seq = p->launch_seq;
   a.lm = d_lm;
   a.use_loss = loss ? 1 : 0;
   a.use_edges = edges ? 1 : 0;
@@ -389,13 +389,16 @@ int partition(clc_problem* p) {
     if (blocks_needed < p->grid) p->grid = (int)blocks_needed;
   }
   const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
-  p->per_warp = std::max<int64_t>(chunk, round_up((p->n_points + n_warps - 1) / n_warps, chunk));
+  // ranges in 64-point units (not whole stages): every warp of the grid gets work, the last stage of a range may be short
+  p->per_warp = std::max<int64_t>(64, round_up((p->n_points + n_warps - 1) / n_warps, 64));
   if (p->warp_first_frame) CLC_CUDA(cudaFreeAsync(p->warp_first_frame, p->stream));
-  if (p->partials) CLC_CUDA(cudaFreeAsync(p->partials, p->stream));
+  if (p->partials_ll) CLC_CUDA(cudaFreeAsync(p->partials_ll, p->stream));
   p->warp_first_frame = nullptr;
-  p->partials = nullptr;
+  p->partials_ll = nullptr;
   CLC_CUDA(cudaMallocAsync(&p->warp_first_frame, sizeof(int) * n_warps, p->stream));
-  CLC_CUDA(cudaMallocAsync(&p->partials, sizeof(double) * (size_t)p->grid * clc::kMaxOut, p->stream));
+  const size_t ll_bytes = sizeof(unsigned long long) * 2 * (size_t)p->grid * clc::kMaxOut;
+  CLC_CUDA(cudaMallocAsync(&p->partials_ll, ll_bytes, p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->partials_ll, 0, ll_bytes, p->stream));  // tag 0 never matches a launch (sequence numbers start at 1)
   const int threads = 256;
   const int blocks = (int)((n_warps + threads - 1) / threads);
   clc::clc_warp_table_kernel<<<blocks, threads, 0, p->stream>>>(p->offsets, p->n_frames, p->n_points, p->per_warp, n_warps,
@@ -446,11 +449,11 @@ int finish_create(clc_problem* p) {
   if (const char* env = std::getenv("CLC_PDL")) p->use_pdl = std::atoi(env) != 0;
   CLC_CUDA(cudaMallocAsync(&p->sums, sizeof(double) * clc::kMaxOut, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->pose, sizeof(double) * 8, p->stream));
-  CLC_CUDA(cudaMallocAsync(&p->ticket, sizeof(unsigned int), p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->launch_seq, sizeof(unsigned int), p->stream));
   CLC_CUDA(cudaMallocAsync(&p->lm, sizeof(clc::LmState), p->stream));
   CLC_CUDA(cudaMallocAsync(&p->p2p_error, sizeof(int), p->stream));
   CLC_CUDA(cudaMemsetAsync(p->p2p_error, 0, sizeof(int), p->stream));
-  CLC_CUDA(cudaMemsetAsync(p->ticket, 0, sizeof(unsigned int), p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->launch_seq, 0, sizeof(unsigned int), p->stream));
   CLC_CUDA(cudaMemsetAsync(p->sums, 0, sizeof(double) * clc::kMaxOut, p->stream));
   p->pinned = pinned_acquire();
   if (!p->pinned) return fail(CLC_ERR_CUDA, "cudaMallocHost failed");
@@ -607,7 +610,7 @@ int clc_problem_destroy(clc_problem* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->stream) {
     void* bufs[] = {p->x, p->y, p->z, p->d_nonplanar, p->frame_pose, p->frame_pose_true, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
-                    p->partials, p->sums, p->pose, p->ticket, p->lm, p->flush_buf, p->p2p_error};
+                    p->partials_ll, p->sums, p->pose, p->launch_seq, p->lm, p->flush_buf, p->p2p_error};
     for (void* b : bufs)
       if (b) cudaFreeAsync(b, p->stream);  // back to the device's memory pool: re-creating a problem is cheap
     cudaStreamSynchronize(p->stream);
@@ -1820,15 +1823,17 @@ int clc_bench_eval(clc_problem* p, const double pose7[7], int n, int flush_l2, f
 // Profiling hook (not part of the reference-facing surface): one sweep with per-block globaltimer stamps.
 // stamps[grid*8]: 0 block start, 1 stream done, 2 tile flushed, 3 block partial written, 4 (last block) final sums,
 // 5 (last block) after the LM update.  with_lm != 0 runs the fused LM update of a fresh LM state at pose7.
+// warp_stamps (optional, [grid * 16]): the time every warp finished its stream.
 int clc_debug_sweep_timing(clc_problem* p, const double pose7[7], int with_lm, int flush_l2, unsigned long long* stamps,
-                           int* grid_out) {
+                           int* grid_out, unsigned long long* warp_stamps) {
   if (!p || !pose7 || !stamps) return fail(CLC_ERR_INVALID, "bad timing arguments");
   int rc = set_device(p);
   if (rc != CLC_OK) return rc;
   if (grid_out) *grid_out = p->grid;
   const size_t bytes = sizeof(unsigned long long) * 8 * (size_t)p->grid;
-  CLC_CUDA(cudaMallocAsync(&p->timing, bytes, p->stream));
-  CLC_CUDA(cudaMemsetAsync(p->timing, 0, bytes, p->stream));
+  const size_t wbytes = sizeof(unsigned long long) * clc::kWarps * (size_t)p->grid;
+  CLC_CUDA(cudaMallocAsync(&p->timing, bytes + wbytes, p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->timing, 0, bytes + wbytes, p->stream));
   if (flush_l2) {
     if (!p->flush_buf) {
       p->flush_n = ((int64_t)256 << 20) / sizeof(double);
@@ -1846,6 +1851,8 @@ int clc_debug_sweep_timing(clc_problem* p, const double pose7[7], int with_lm, i
   CLC_CUDA(cudaMemcpyAsync(p->pose, pose7, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
   rc = launch_sweep(p, clc::kModeLM, p->use_loss != 0, p->n_edges > 0, p->pose, nullptr, with_lm ? p->lm : nullptr, /*collective=*/false);
   cudaError_t e = cudaMemcpyAsync(stamps, p->timing, bytes, cudaMemcpyDeviceToHost, p->stream);
+  if (e == cudaSuccess && warp_stamps)
+    e = cudaMemcpyAsync(warp_stamps, p->timing + 8 * (size_t)p->grid, wbytes, cudaMemcpyDeviceToHost, p->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
   cudaFreeAsync(p->timing, p->stream);
   p->timing = nullptr;

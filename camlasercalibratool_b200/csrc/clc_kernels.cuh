@@ -74,7 +74,7 @@ struct ProblemView {
   int64_t n_frames;
   int64_t n_points;
   int64_t n_edges;            // 2 * n_frames or 0
-  int64_t per_warp;           // points per warp (multiple of the kernel family's stage size)
+  int64_t per_warp;           // points per warp (multiple of 64)
   double inv_a2;              // 1 / cauchy_a^2
   double a2;                  // cauchy_a^2
 };
@@ -82,13 +82,15 @@ struct ProblemView {
 struct SweepArgs {
   const double* pose7;        // device pointer: the pose to evaluate
   const int* done;            // device flag: non-zero -> the sweep is a no-op (LM finished); may be nullptr
-  double* partials;           // [gridDim.x * kMaxOut]
+  unsigned long long* partials_ll;  // [gridDim.x * kMaxOut * 2] block partial sums, every 8-byte word = 32 payload bits +
+                                    // the 32-bit sequence number of the launch (no ticket, no fence: see the block reduction)
   double* sums;               // [kMaxOut] result of the launch
-  unsigned int* ticket;       // last-block-done counter (self-resetting)
+  unsigned int* launch_seq;   // sweeps completed on this problem (device counter, bumped by block 0 of every real sweep)
   LmState* lm;                // non-null: the last block also runs lm_update (single-rank fused mode)
   int use_loss;
   int use_edges;
-  unsigned long long* timing;  // optional [gridDim.x * 8] globaltimer stamps (profiling hook), nullptr normally
+  unsigned long long* timing;  // optional [gridDim.x * 8] globaltimer stamps (profiling hook), nullptr normally;
+                               // followed by [gridDim.x * kWarps] per-warp "stream done" stamps
   // fused all-reduce over NVLink peer memory (nranks > 1): every rank's last block stores its sums into every rank's
   // mailbox with a low-latency protocol -- every 8-byte word carries 32 bits of payload and the 32-bit sequence number,
   // 8-byte stores are atomic, so no fence and no separate flag are needed -- then polls its own mailbox and adds the
@@ -148,6 +150,14 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
   unsigned long long v;
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+
+// 16-byte store / load of two tagged words (each word carries its own tag, so the pair need not be atomic)
+__device__ __forceinline__ void st_volatile_v2(unsigned long long* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_volatile_v2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
@@ -317,14 +327,21 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   double* tile = reinterpret_cast<double*>(s_dyn) + kWarps * RING + warp * kTileDoublesPerWarp;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (size_t)kWarps * (RING + kTileDoublesPerWarp) * 8) + warp * kBarsPerWarp;
 
+  // points of stage c: full stages except possibly the last one of the range, which is cut to whole 64-point groups (the
+  // ranges are handed out in 64-point units so that every warp of the grid gets work; the arrays are zero padded)
+  auto chunk_len = [&](int c) -> int {
+    const int64_t left = p1 - (p0 + (int64_t)c * CH);
+    return left >= CH ? CH : (int)((left + 63) & ~(int64_t)63);
+  };
   auto issue_chunk = [&](int c) {  // lane 0 only
     const int st = c % NST;
     double* dst = ring + st * SST;
     const int64_t src = p0 + (int64_t)c * CH;  // multiple of 64 points -> 512 B aligned
-    mbar_expect_tx(bars + st, (PLANAR ? 2 : 3) * CH * 8);
-    bulk_g2s(dst, pv.x + src, CH * 8, bars + st);
-    bulk_g2s(dst + CH, pv.y + src, CH * 8, bars + st);
-    if (!PLANAR) bulk_g2s(dst + 2 * CH, pv.z + src, CH * 8, bars + st);
+    const int len = chunk_len(c);
+    mbar_expect_tx(bars + st, (PLANAR ? 2 : 3) * len * 8);
+    bulk_g2s(dst, pv.x + src, len * 8, bars + st);
+    bulk_g2s(dst + CH, pv.y + src, len * 8, bars + st);
+    if (!PLANAR) bulk_g2s(dst + 2 * CH, pv.z + src, len * 8, bars + st);
   };
   if (lane == 0) {
 #pragma unroll
@@ -332,6 +349,18 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int c = 0; c < NST && c < n_chunks; ++c) issue_chunk(c);
+  }
+  if (n_chunks > 0 && n_chunks <= NST) {
+    // a short last stage of a range that never filled this ring slot before: the lanes beyond it are masked out of every
+    // sum, but they are still multiplied by a zero weight -- give them finite values (in longer ranges the slot holds the
+    // points of an earlier stage)
+    const int last = n_chunks - 1, len = chunk_len(last);
+    double* dst = ring + (last % NST) * SST;
+    for (int i = len + lane; i < CH; i += 32) {
+      dst[i] = 0.0;
+      dst[CH + i] = 0.0;
+      if (!PLANAR) dst[2 * CH + i] = 0.0;
+    }
   }
   __syncwarp();
 
@@ -347,6 +376,8 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   }
 
   for (int k = lane; k < NOUT; k += 32) s_acc[warp][k] = 0.0;
+  // sequence number of this sweep (the previous sweep on this problem has completed: griddepcontrol.wait above)
+  const unsigned int launch_tag = __ldcg(args.launch_seq) + 1u;
 
   PoseConsts pc;
   {
@@ -522,6 +553,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     if (open) park_piece();  // the last frame continues in the next warp's range
   }
   CLC_STAMP(1);
+  if (args.timing != nullptr && lane == 0) args.timing[(int64_t)gridDim.x * 8 + gwarp] = globaltimer_ns();
   flush_tile();
   CLC_STAMP(2);
 
@@ -563,105 +595,124 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   }
 
   // ---- block reduction (fixed order) ----
+  // The block's partial sums travel to block 0 with a low-latency protocol instead of "store, fence, ticket": every
+  // 8-byte word carries 32 bits of the value and the 32-bit sequence number of this launch, 8-byte stores are single
+  // transactions, so the reader needs no flag and the writer no fence -- one one-way trip through L2 instead of three
+  // dependent ones (partials -> release ticket -> acquire poll -> partial loads).
+  const unsigned long long ll_tag = (unsigned long long)launch_tag << 32;
   __syncthreads();
   if (threadIdx.x < NOUT) {
     double v = 0.0;
 #pragma unroll
     for (int wv = 0; wv < kWarps; ++wv) v += s_acc[wv][threadIdx.x];
-    __stcg(args.partials + (int64_t)blockIdx.x * kMaxOut + threadIdx.x, v);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    st_volatile_v2(args.partials_ll + ((int64_t)blockIdx.x * kMaxOut + threadIdx.x) * 2, ll_tag | (bits & 0xffffffffull),
+                   ll_tag | (bits >> 32));
   }
-  __syncthreads();
   CLC_STAMP(3);
-  // Every block releases its partial sums with a ticket.  The final reduction (and the LM update) always runs on block 0
-  // -- the persistent grid is fully co-resident, so block 0 can wait for the other tickets -- rather than on whichever
-  // block happens to finish last: the ~1000 instructions of that serial tail then stay warm in ONE SM's instruction
-  // cache from launch to launch instead of being fetched cold from L2 by a different SM every time.
-  if (threadIdx.x == 0) atom_add_acq_rel_gpu(args.ticket, 1u);
   // let the next sweep's blocks be scheduled on the SMs this grid is vacating (they only prefetch until we complete)
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // The final reduction (and the LM update) always runs on block 0 -- the persistent grid is fully co-resident, so
+  // block 0 can wait for the other blocks -- rather than on whichever block happens to finish last: the ~1000 instructions
+  // of that serial tail then stay warm in ONE SM's instruction cache from launch to launch.
   if (blockIdx.x != 0) return;
-  if (threadIdx.x == 0) {
-    // The grid is sized to be fully co-resident (one block per SM), which is what lets block 0 wait here.  Should that ever
-    // not hold (MPS with a reduced SM share, a foreign kernel pinning SMs), fail loudly instead of hanging: after 2 s the
-    // error flag is raised, the host reports it and the LM is stopped.
-    unsigned int polls = 0;
-    unsigned long long t0 = 0;
-    while (ld_acquire_gpu(args.ticket) != gridDim.x) {
-      if ((++polls & 0x3ffu) == 0u) {
-        const unsigned long long now = globaltimer_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 2000000000ull) {
-          if (args.error != nullptr) *args.error = 2;
-          break;
-        }
-      }
-    }
-  }
-  __syncthreads();
 
   // ---- block 0: deterministic sum of the block partials ----
   {
-    // warp wv sums blocks wv, wv+8, ...; lane handles output `lane` (and lane+32 for the 54-wide mode).  The loads
-    // of a round are independent L2 round trips issued back to back; the additions keep the block order.
-    constexpr int kRound = 20;
-    for (int k = lane; k < NOUT; k += 32) {
-      double v = 0.0;
-      for (int b = warp; b < (int)gridDim.x; b += kRound * kWarps) {
-        double t[kRound];
+    // thread (part, k) polls the words of output k of blocks part, part + PARTS, ... (all its loads in flight at once)
+    // and adds them in block order; the PARTS partial results are then added in part order: a fixed tree.
+    constexpr int PARTS = kThreads / NOUT;
+    constexpr int NB = 10;  // blocks per thread and round
+    double* s_gather = &s_red[0][0];
+    static_assert(kWarps * 32 >= PARTS * NOUT, "s_red holds one value per gathering thread");
+    if (threadIdx.x < PARTS * NOUT) {
+      const int k = threadIdx.x % NOUT, part = threadIdx.x / NOUT;
+      double acc = 0.0;
+      for (int base = part; base < (int)gridDim.x; base += PARTS * NB) {
+        unsigned long long w0[NB], w1[NB];
+        unsigned int pending = 0u;
 #pragma unroll
-        for (int u = 0; u < kRound; ++u) {
-          const int bb = b + u * kWarps;
-          t[u] = (bb < (int)gridDim.x) ? __ldcg(args.partials + (int64_t)bb * kMaxOut + k) : 0.0;
+        for (int u = 0; u < NB; ++u)
+          if (base + u * PARTS < (int)gridDim.x) pending |= 1u << u;
+        unsigned int polls = 0;
+        unsigned long long t0 = 0;
+        while (pending != 0u) {
+#pragma unroll
+          for (int u = 0; u < NB; ++u)
+            if ((pending >> u) & 1u)
+              ld_volatile_v2(args.partials_ll + ((int64_t)(base + u * PARTS) * kMaxOut + k) * 2, w0[u], w1[u]);
+#pragma unroll
+          for (int u = 0; u < NB; ++u)
+            if (((pending >> u) & 1u) && (w0[u] & 0xffffffff00000000ull) == ll_tag && (w1[u] & 0xffffffff00000000ull) == ll_tag)
+              pending &= ~(1u << u);
+          if (pending != 0u && (++polls & 0xffu) == 0u) {
+            // The grid is sized to be fully co-resident (one block per SM), which is what lets block 0 wait here.  Should
+            // that ever not hold (MPS with a reduced SM share, a foreign kernel pinning SMs), fail loudly instead of
+            // hanging: after 2 s the error flag is raised, the host reports it and the LM is stopped.
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) {
+              if (args.error != nullptr) *args.error = 2;
+              break;
+            }
+          }
         }
 #pragma unroll
-        for (int u = 0; u < kRound; ++u) v += t[u];
+        for (int u = 0; u < NB; ++u)
+          if (base + u * PARTS < (int)gridDim.x) acc += __longlong_as_double((long long)((w1[u] << 32) | (w0[u] & 0xffffffffull)));
       }
-      if (k < 32) s_red[warp][k] = v; else s_acc[warp][k] = v;
+      s_gather[threadIdx.x] = acc;
     }
     __syncthreads();
     double total = 0.0;
     if (threadIdx.x < NOUT) {
-      const int k = threadIdx.x;
 #pragma unroll
-      for (int wv = 0; wv < kWarps; ++wv) total += (k < 32) ? s_red[wv][k] : s_acc[wv][k];
+      for (int part = 0; part < PARTS; ++part) total += s_gather[part * NOUT + threadIdx.x];
     }
     if (args.nranks > 1) {
-      // ---- fused all-reduce: NVLink stores into every rank's mailbox, flags, deterministic rank-order sum ----
+      // ---- fused all-reduce: NVLink stores into every rank's mailbox, tagged words, deterministic rank-order sum ----
       // the sequence number lives on the device: sweeps that no-op (LM already finished) must not consume one, or two
       // consecutive real exchanges could land in the same parity slot while a slow peer is still reading it
+      double* s_tot = s_acc[0];                                 // [NOUT] this rank's totals
+      double* s_x = reinterpret_cast<double*>(s_dyn);           // [nranks][NOUT] (the rings are idle by now)
+      __syncthreads();                                          // s_gather reads are done before s_acc/s_dyn are reused
+      if (threadIdx.x < NOUT) s_tot[threadIdx.x] = total;
+      __syncthreads();
       const unsigned long long seq = *args.seq_counter + 1ull;
       const unsigned long long tag = (seq & 0xffffffffull) << 32;  // never matches the zero-initialised mailbox for seq >= 1
       const int par = (int)(seq & 1ull);
-      if (threadIdx.x < NOUT) {
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(total);
-        const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
-        const int64_t slot = (((int64_t)par * args.nranks + args.rank) * kMailboxSlot + threadIdx.x) * 2;
-        for (int r = 0; r < args.nranks; ++r) {
-          st_relaxed_sys(args.peer_mailbox[r] + slot, w0);
-          st_relaxed_sys(args.peer_mailbox[r] + slot + 1, w1);
-        }
-        // poll my own mailbox: the contribution of every rank, added in rank order
-        const unsigned long long t0 = globaltimer_ns();
-        total = 0.0;
-        bool timed_out = false;
-        for (int r = 0; r < args.nranks && !timed_out; ++r) {
-          const unsigned long long* src =
-              args.peer_mailbox[args.rank] + (((int64_t)par * args.nranks + r) * kMailboxSlot + threadIdx.x) * 2;
-          unsigned long long a0, a1;
-          for (;;) {
-            a0 = ld_relaxed_sys(src);
-            a1 = ld_relaxed_sys(src + 1);
-            if ((a0 & 0xffffffff00000000ull) == tag && (a1 & 0xffffffff00000000ull) == tag) break;
-            if (globaltimer_ns() - t0 > 5000000000ull) {  // 5 s: a peer died -- fail loudly instead of hanging
-              if (args.error != nullptr) *args.error = 1;
-              timed_out = true;
-              break;
-            }
+      const int n_words = args.nranks * NOUT;
+      // one (destination rank, output) pair per thread: all stores leave at once
+      for (int idx = threadIdx.x; idx < n_words; idx += kThreads) {
+        const int r = idx / NOUT, k = idx % NOUT;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(s_tot[k]);
+        const int64_t slot = (((int64_t)par * args.nranks + args.rank) * kMailboxSlot + k) * 2;
+        st_relaxed_sys(args.peer_mailbox[r] + slot, tag | (bits & 0xffffffffull));
+        st_relaxed_sys(args.peer_mailbox[r] + slot + 1, tag | (bits >> 32));
+      }
+      // one (source rank, output) pair per thread polls my own mailbox: the waits for all ranks overlap
+      const unsigned long long t0 = globaltimer_ns();
+      for (int idx = threadIdx.x; idx < n_words; idx += kThreads) {
+        const int r = idx / NOUT, k = idx % NOUT;
+        const unsigned long long* src = args.peer_mailbox[args.rank] + (((int64_t)par * args.nranks + r) * kMailboxSlot + k) * 2;
+        unsigned long long a0, a1;
+        unsigned int polls = 0;
+        for (;;) {
+          a0 = ld_relaxed_sys(src);
+          a1 = ld_relaxed_sys(src + 1);
+          if ((a0 & 0xffffffff00000000ull) == tag && (a1 & 0xffffffff00000000ull) == tag) break;
+          if ((++polls & 0x3fu) == 0u && globaltimer_ns() - t0 > 5000000000ull) {  // 5 s: a peer died -- fail loudly
+            if (args.error != nullptr) *args.error = 1;
+            break;
           }
-          total += __longlong_as_double((long long)((a1 << 32) | (a0 & 0xffffffffull)));
         }
+        s_x[idx] = __longlong_as_double((long long)((a1 << 32) | (a0 & 0xffffffffull)));
       }
       __syncthreads();
+      if (threadIdx.x < NOUT) {
+        total = 0.0;
+        for (int r = 0; r < args.nranks; ++r) total += s_x[r * NOUT + threadIdx.x];  // rank order: identical bits everywhere
+      }
       if (threadIdx.x == 0) *args.seq_counter = seq;
     }
     __syncthreads();
@@ -671,7 +722,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     }
     __syncthreads();
     CLC_STAMP(4);
-    if (threadIdx.x == 0) *args.ticket = 0u;
+    if (threadIdx.x == 0) *args.launch_seq = launch_tag;
     if (MODE == kModeLM && args.lm != nullptr) {
       // stage the hot LM state through shared memory: one parallel round trip in, one out, instead of one per field
       unsigned long long* s_core = reinterpret_cast<unsigned long long*>(s_dyn);  // the rings are idle by now

@@ -30,6 +30,8 @@
 #include "LaseCamCalCeres.h"
 #include "clc_b200.h"
 
+extern "C" void clc_dropin_last_phases(double out[7]);  // host/LaseCamCalB200.cpp
+
 namespace {
 
 double now_ms() {
@@ -113,7 +115,7 @@ int main(int argc, char** argv) {
   double ref_pose[7] = {0, 0, 0, 0, 0, 0, 1}, lm_device_ms = 0.0;
   int64_t h2d_bytes = 0;
   int pack_threads = 0, upload_chunks = 0, upload_direct = 0;
-  double upload_ms = 0.0, upload_pack_wait_ms = 0.0;
+  double upload_ms = 0.0, upload_pack_wait_ms = 0.0;  // (first upload of the process: includes the one-time pinned-ring allocation)
   {
     std::vector<double> fp(7 * (size_t)frames), ep;
     std::vector<const double*> fpts((size_t)frames);
@@ -177,7 +179,11 @@ int main(int argc, char** argv) {
   }
 
   // ---- timed calls ----
-  std::vector<double> ms_moved, ms_lvalue;
+  // body_*: entry to return of CamLaserCalibration() (measured inside the drop-in: marshal + gather/pack + PCIe + HBM layout +
+  // LM solve + report + analysis tail + tear-down) -- the headline.  call_*: the whole call expression on the caller's clock,
+  // which adds what the by-value `obs` parameter costs the caller (move or deep copy before entry, destruction after return).
+  std::vector<double> body, call_moved, call_lvalue, body_lvalue;
+  double phase_sum[7] = {0, 0, 0, 0, 0, 0, 0};
   double max_dev = 0.0;
   for (int it = 0; it < warmup + steps; ++it) {
     Eigen::Matrix4d Tcl = Eigen::Matrix4d::Identity();
@@ -189,7 +195,13 @@ int main(int argc, char** argv) {
       CamLaserCalibration(std::move(copy), Tcl, lfd, edges != 0);
       t1 = now_ms();
     }
-    if (it >= warmup) ms_moved.push_back(t1 - t0);
+    double ph[7];
+    clc_dropin_last_phases(ph);
+    if (it >= warmup) {
+      call_moved.push_back(t1 - t0);
+      body.push_back(ph[6]);
+      for (int k = 0; k < 7; ++k) phase_sum[k] += ph[k];
+    }
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 4; ++c) max_dev = std::max(max_dev, std::fabs(Tcl(r, c) - ref_T[r * 4 + c]));
   }
@@ -203,22 +215,29 @@ int main(int argc, char** argv) {
       CamLaserCalibration(obs, Tcl, lfd, edges != 0);
       t1 = now_ms();
     }
-    if (it >= 1) ms_lvalue.push_back(t1 - t0);
+    double ph[7];
+    clc_dropin_last_phases(ph);
+    if (it >= 1) { call_lvalue.push_back(t1 - t0); body_lvalue.push_back(ph[6]); }
   }
   double sum = 0.0;
-  for (double v : ms_moved) sum += v;
-  const double mean_moved = sum / (double)ms_moved.size();
+  for (double v : body) sum += v;
+  const double mean_body = sum / (double)body.size();
+  for (int k = 0; k < 7; ++k) phase_sum[k] /= (double)body.size();
   const int sweeps_per_call = lm_sweeps + 1;  // + the un-robustified information sweep of the analysis tail (:318-362)
   std::printf(
       "CLC_DROPIN_JSON {\"frames\": %lld, \"beams\": %lld, \"points\": %lld, \"edges\": %d, \"n_devices\": %d, \"steps\": %d, \"warmup\": %d, "
-      "\"ms_per_call_mean\": %.6f, \"ms_per_call_median\": %.6f, \"ms_per_call_min\": %.6f, \"ms_per_call_max\": %.6f, "
-      "\"ms_per_call_lvalue_median\": %.6f, \"sweeps_per_call\": %d, \"lm_iterations\": %d, \"termination\": %d, "
+      "\"body_ms_mean\": %.6f, \"body_ms_median\": %.6f, \"body_ms_min\": %.6f, \"body_ms_max\": %.6f, "
+      "\"phases_ms\": {\"marshal\": %.4f, \"upload\": %.4f, \"solve\": %.4f, \"report\": %.4f, \"information\": %.4f, \"destroy\": %.4f}, "
+      "\"call_expr_moved_ms_median\": %.6f, \"call_expr_lvalue_ms_median\": %.6f, \"body_ms_in_lvalue_calls_median\": %.6f, "
+      "\"caller_copy_of_obs_ms\": %.6f, \"caller_destruction_of_obs_ms\": %.6f, "
+      "\"sweeps_per_call\": %d, \"lm_iterations\": %d, \"termination\": %d, "
       "\"lm_device_ms\": %.6f, \"h2d_bytes_per_call\": %lld, \"d2h_bytes_per_call\": %d, \"raw_h2d_ms_same_bytes\": %.6f, "
-      "\"upload_ms\": %.6f, \"upload_pack_wait_ms\": %.6f, \"upload_chunks\": %d, \"pack_threads\": %d, \"upload_direct\": %d, "
-      "\"caller_copy_of_obs_ms\": %.6f, \"caller_destruction_of_obs_ms\": %.6f, \"max_abs_dev_vs_c_abi_solve\": %.3e}\n",
-      (long long)frames, (long long)beams, (long long)n_points, edges, n_devices, steps, warmup, mean_moved, median(ms_moved),
-      *std::min_element(ms_moved.begin(), ms_moved.end()), *std::max_element(ms_moved.begin(), ms_moved.end()),
-      median(ms_lvalue), sweeps_per_call, lm_iterations, termination, lm_device_ms, (long long)h2d_bytes,
-      (int)clc_solve_readback_bytes() + 28 * 8, raw_h2d_ms, upload_ms, upload_pack_wait_ms, upload_chunks, pack_threads, upload_direct, copy_ms, destroy_ms, max_dev);
+      "\"upload_chunks\": %d, \"pack_threads\": %d, \"upload_direct\": %d, \"max_abs_dev_vs_c_abi_solve\": %.3e}\n",
+      (long long)frames, (long long)beams, (long long)n_points, edges, n_devices, steps, warmup, mean_body, median(body),
+      *std::min_element(body.begin(), body.end()), *std::max_element(body.begin(), body.end()),
+      phase_sum[0], phase_sum[1], phase_sum[2], phase_sum[3], phase_sum[4], phase_sum[5],
+      median(call_moved), median(call_lvalue), median(body_lvalue), copy_ms, destroy_ms,
+      sweeps_per_call, lm_iterations, termination, lm_device_ms, (long long)h2d_bytes,
+      (int)clc_solve_readback_bytes() + 28 * 8, raw_h2d_ms, upload_chunks, pack_threads, upload_direct, max_dev);
   return max_dev < 1e-9 ? 0 : 3;
 }

@@ -388,14 +388,17 @@ int oracle_evaluate_normal(const oracle_problem* p, const double pose7[7], doubl
 /* ------------------------------------------------------------------------------------------------------ */
 
 /* In-place Householder triangularisation of the rows x 6 row-major A (rows >= 6) and of the rhs b: on exit the
- * top 6 x 6 of A is R and b[0..5] is (Q^T b)[0..5].  Returns non-zero for a zero column. */
+ * top 6 x 6 of A is R and b[0..5] is (Q^T b)[0..5].  A column that is exactly zero from the diagonal down needs no
+ * reflection (R_kk = 0, as in Eigen's HouseholderQR, where tau = 0); that is not a failure here: in the blocked use
+ * below, a Jacobian column that is identically zero (the reference's "ONLY pitch" boards, main/calibr_simulation.cpp:50:
+ * every n_y == 0) becomes non-zero once the LM diagonal rows are stacked under it.  Always returns 0. */
 static int hh_factor6(double* A, double* b, int64_t rows) {
   const int n = 6;
   for (int k = 0; k < n; ++k) {
     double nrm2 = 0.0;
     for (int64_t i = k; i < rows; ++i) nrm2 += A[i * n + k] * A[i * n + k];
     const double nrm = sqrt(nrm2);
-    if (!(nrm > 0.0)) return 1;
+    if (!(nrm > 0.0)) { A[(int64_t)k * n + k] = 0.0; continue; }
     const double akk = A[(int64_t)k * n + k];
     const double alpha = akk > 0.0 ? -nrm : nrm;
     /* v = x - alpha e1 (stored in column k below the diagonal, v0 separately); beta = 2 / v^T v */
