@@ -255,6 +255,7 @@ struct clc_problem {
   int64_t flush_n = 0;
   unsigned long long* timing = nullptr;  // profiling hook (clc_debug_sweep_timing)
   bool use_pdl = true;                   // CLC_PDL=0 disables programmatic dependent launch in the LM loop
+  bool loop_in_kernel = true;            // CLC_LOOP_IN_KERNEL=0: one launch per LM iteration also for single-block problems
   // pinned host mirrors (views into one pooled block)
   PinnedBlock* pinned = nullptr;
   double* h_sums = nullptr;
@@ -305,7 +306,7 @@ int set_device(const clc_problem* p) {
 // one K1 launch on the problem's stream
 // collective: the sums of this launch are to be all-reduced (in-kernel when the peer path is active)
 int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* d_pose, const int* d_done,
-                 clc::LmState* d_lm, bool collective = true, bool pdl = false) {
+                 clc::LmState* d_lm, bool collective = true, bool pdl = false, int loop_sweeps = 1) {
   clc::SweepArgs a;
   a.pose7 = d_pose;
   a.done = d_done;
@@ -315,6 +316,7 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
   a.lm = d_lm;
   a.use_loss = loss ? 1 : 0;
   a.use_edges = edges ? 1 : 0;
+  a.loop_sweeps = loop_sweeps;
   a.timing = p->timing;
   a.nranks = 1;
   a.rank = 0;
@@ -344,6 +346,11 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
   if (mode == clc::kModeClosedForm) {
     le = p->planar ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeClosedForm, true>, v, a)
                    : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeClosedForm, false>, v, a);
+  } else if (loop_sweeps > 1) {
+    // single-block problems: the instantiation that loops the LM in the kernel (never planar: those engage on large data only)
+    if (p->planar || p->grid != 1 || d_lm == nullptr) return fail(CLC_ERR_INVALID, "internal: looping sweep on a multi-block / planar problem");
+    le = loss ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, false, true>, v, a)
+              : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeLM, false, true>, v, a);
   } else if (loss) {
     le = p->planar ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, true>, v, a)
                    : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, false>, v, a);
@@ -387,6 +394,11 @@ int partition(clc_problem* p) {
     const int64_t stages = (p->n_points + chunk - 1) / chunk;
     const int64_t blocks_needed = std::max<int64_t>(1, (stages + clc::kWarps - 1) / clc::kWarps);
     if (blocks_needed < p->grid) p->grid = (int)blocks_needed;
+    // the reference's own sizes (50 boards x 180 beams, reference main/calibr_simulation.cpp:34,79) fit ONE block: a
+    // single-block grid lets the kernel run the whole LM loop by itself (no launch, no inter-block exchange per iteration)
+    int64_t single_block_max = (int64_t)clc::kWarps * 8 * clc::kChunk;  // up to 8 stages per warp and sweep (16384 points)
+    if (const char* env = std::getenv("CLC_SINGLE_BLOCK_MAX_POINTS")) single_block_max = std::atoll(env);
+    if (p->n_points <= single_block_max) p->grid = 1;
   }
   const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
   // ranges in 64-point units (not whole stages): every warp of the grid gets work, the last stage of a range may be short
@@ -428,8 +440,11 @@ int finish_create(clc_problem* p) {
     const void* variants[] = {
         (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, false>,         (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, true>,
         (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, false>,        (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, true>,
-        (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, false>, (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, true>};
-    for (int v = 0; v < 6; ++v) {
+        (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, false>, (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, true>,
+        (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, false, true>,   nullptr,
+        (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, false, true>,  nullptr};
+    for (int v = 0; v < 10; ++v) {
+      if (variants[v] == nullptr) continue;
       const void* fn = variants[v];
       const int smem = clc::dyn_smem_bytes((v & 1) != 0);  // odd entries are the planar instantiations
       CLC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -447,6 +462,7 @@ int finish_create(clc_problem* p) {
   }
   p->grid_full = p->num_sms * blocks_per_sm;
   if (const char* env = std::getenv("CLC_PDL")) p->use_pdl = std::atoi(env) != 0;
+  if (const char* env = std::getenv("CLC_LOOP_IN_KERNEL")) p->loop_in_kernel = std::atoi(env) != 0;
   CLC_CUDA(cudaMallocAsync(&p->sums, sizeof(double) * clc::kMaxOut, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->pose, sizeof(double) * 8, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->launch_seq, sizeof(unsigned int), p->stream));
@@ -1085,13 +1101,13 @@ int solve_begin(clc_problem* p, const double pose7[7], const clc_lm_options& opt
 }
 
 // one LM iteration: the fused sweep (+ NCCL all-reduce and the LM kernel when the exchange is not fused)
-int solve_launch_one(clc_problem* p, SolveCtx* ctx) {
+int solve_launch_one(clc_problem* p, SolveCtx* ctx, int loop_sweeps = 1) {
   int rc = set_device(p);
   if (rc != CLC_OK) return rc;
   // fused mode: one kernel per LM iteration, chained with programmatic dependent launch (the next sweep prefetches
   // its first stages while this one's block 0 reduces and updates)
   rc = launch_sweep(p, clc::kModeLM, ctx->loss, ctx->edges, p->lm->core.cand, &p->lm->core.done,
-                    ctx->fused_update ? p->lm : nullptr, /*collective=*/true, /*pdl=*/ctx->fused_update && p->use_pdl);
+                    ctx->fused_update ? p->lm : nullptr, /*collective=*/true, /*pdl=*/ctx->fused_update && p->use_pdl, loop_sweeps);
   if (rc != CLC_OK) return rc;
   if (!ctx->fused_update) {
     rc = allreduce_sums(p, clc::kNumSums);
@@ -1155,6 +1171,12 @@ int solve_all(clc_problem* const* ps, int n, double pose7[7], const clc_lm_optio
   if (rc != CLC_OK) return rc;
   const int max_sweeps = ctx[0].max_sweeps;
   int launched = 0;
+  if (n == 1 && ps[0]->grid == 1 && ctx[0].fused_update && ps[0]->nranks <= 1 && ps[0]->loop_in_kernel) {
+    // a problem that fits one block: ONE launch runs the whole LM loop (sweep, reduce, lm_update, next sweep)
+    rc = solve_launch_one(ps[0], &ctx[0], max_sweeps);
+    if (rc != CLC_OK) return rc;
+    launched = max_sweeps;
+  }
   while (launched < max_sweeps) {
     const int batch = std::min(opt.iterations_per_sync, max_sweeps - launched);
     // iteration-major order: sweep i of every shard is queued before sweep i+1 of any, so no device's queue can fill up

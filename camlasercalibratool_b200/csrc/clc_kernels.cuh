@@ -89,6 +89,8 @@ struct SweepArgs {
   LmState* lm;                // non-null: the last block also runs lm_update (single-rank fused mode)
   int use_loss;
   int use_edges;
+  int loop_sweeps;            // > 1 (single-block grids with a fused LM update only): the kernel runs up to that many LM
+                              // iterations by itself -- sweep, reduce, lm_update, next sweep -- instead of one per launch
   unsigned long long* timing;  // optional [gridDim.x * 8] globaltimer stamps (profiling hook), nullptr normally;
                                // followed by [gridDim.x * kWarps] per-warp "stream done" stamps
   // fused all-reduce over NVLink peer memory (nranks > 1): every rank's last block stores its sums into every rank's
@@ -290,7 +292,9 @@ __device__ __forceinline__ void renormalise(Moments& a) {
 // per lane -- into the 28 normal-equation sums, which are shuffle-reduced into the warp's accumulator.  Block
 // partials go to global memory; the last block to finish (ticket) adds them in a fixed order, so the result is
 // bit-reproducible from run to run, and optionally runs the LM update.
-template <bool LOSS, int MODE, bool PLANAR>
+// LOOP: the instantiation for single-block grids that runs the whole LM loop inside one launch (args.loop_sweeps sweeps at
+// most); kept apart so that the streaming instantiations do not carry the loop's bookkeeping in registers.
+template <bool LOSS, int MODE, bool PLANAR, bool LOOP = false>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   constexpr int NOUT = (MODE == kModeLM) ? kNumSums : kMaxOut;
@@ -304,6 +308,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
   __shared__ double s_acc[kWarps][NOUT];
   __shared__ double s_red[kWarps][32];
+  __shared__ unsigned long long s_core[kLmCoreWords];  // block 0: the hot LM state
 
   CLC_STAMP(0);
   if (args.timing != nullptr && threadIdx.x == 0) {
@@ -333,34 +338,52 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     const int64_t left = p1 - (p0 + (int64_t)c * CH);
     return left >= CH ? CH : (int)((left + 63) & ~(int64_t)63);
   };
-  auto issue_chunk = [&](int c) {  // lane 0 only
-    const int st = c % NST;
-    double* dst = ring + st * SST;
-    const int64_t src = p0 + (int64_t)c * CH;  // multiple of 64 points -> 512 B aligned
-    const int len = chunk_len(c);
-    mbar_expect_tx(bars + st, (PLANAR ? 2 : 3) * len * 8);
-    bulk_g2s(dst, pv.x + src, len * 8, bars + st);
-    bulk_g2s(dst + CH, pv.y + src, len * 8, bars + st);
-    if (!PLANAR) bulk_g2s(dst + 2 * CH, pv.z + src, len * 8, bars + st);
+  // Stage slots and mbarrier phases follow a running count of issued stages (`issued`, kept by every lane), so that a kernel
+  // that loops over several sweeps (loop_sweeps > 1) keeps prefetching across the reduce + LM update between two sweeps.
+  const int sweeps_max = (LOOP && args.loop_sweeps > 1 && gridDim.x == 1 && MODE == kModeLM && args.lm != nullptr) ? args.loop_sweeps : 1;
+  const int total_chunks = LOOP ? sweeps_max * n_chunks : n_chunks;
+  int issued = 0, next_c = 0;  // next_c == issued mod n_chunks
+  auto issue_one = [&](bool slot_was_read) {
+    if (lane == 0) {
+      const int c = LOOP ? next_c : issued, st = issued % NST;
+      double* dst = ring + st * SST;
+      const int64_t src = p0 + (int64_t)c * CH;  // multiple of 64 points -> 512 B aligned
+      const int len = chunk_len(c);
+      if (slot_was_read) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bars + st, (PLANAR ? 2 : 3) * len * 8);
+      bulk_g2s(dst, pv.x + src, len * 8, bars + st);
+      bulk_g2s(dst + CH, pv.y + src, len * 8, bars + st);
+      if (!PLANAR) bulk_g2s(dst + 2 * CH, pv.z + src, len * 8, bars + st);
+    }
+    ++issued;
+    if (LOOP && ++next_c == n_chunks) next_c = 0;
+  };
+  // waits for the stages that are still in flight (g = first stage not yet consumed): a block must not exit before its bulk
+  // copies have landed
+  auto drain = [&](int g) {
+    for (; g < issued; ++g) mbar_wait(bars + g % NST, (uint32_t)(g / NST) & 1u);
   };
   if (lane == 0) {
 #pragma unroll
     for (int st = 0; st < NST; ++st) mbar_init(bars + st, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int c = 0; c < NST && c < n_chunks; ++c) issue_chunk(c);
   }
-  if (n_chunks > 0 && n_chunks <= NST) {
-    // a short last stage of a range that never filled this ring slot before: the lanes beyond it are masked out of every
+  __syncwarp();
+  for (int g = 0; g < NST && g < total_chunks; ++g) {
+    // A short last stage that is the first thing ever copied into its ring slot: the lanes beyond it are masked out of every
     // sum, but they are still multiplied by a zero weight -- give them finite values (in longer ranges the slot holds the
-    // points of an earlier stage)
-    const int last = n_chunks - 1, len = chunk_len(last);
-    double* dst = ring + (last % NST) * SST;
-    for (int i = len + lane; i < CH; i += 32) {
-      dst[i] = 0.0;
-      dst[CH + i] = 0.0;
-      if (!PLANAR) dst[2 * CH + i] = 0.0;
+    // points of an earlier stage).
+    const int len = chunk_len(LOOP ? next_c : issued);
+    if (len < CH) {
+      double* dst = ring + g * SST;
+      for (int i = len + lane; i < CH; i += 32) {
+        dst[i] = 0.0;
+        dst[CH + i] = 0.0;
+        if (!PLANAR) dst[2 * CH + i] = 0.0;
+      }
     }
+    issue_one(false);
   }
   __syncwarp();
 
@@ -370,23 +393,19 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (args.done != nullptr && (*args.done != 0 || (args.error != nullptr && *args.error != 0))) {
     // the LM finished (or an earlier sweep of this solve lost a peer): nothing to do, but the bulk copies already in flight must land before the block may exit
-    const int issued = n_chunks < NST ? n_chunks : NST;
-    for (int c = 0; c < issued; ++c) mbar_wait(bars + c, 0u);
+    drain(0);
     return;
   }
 
-  for (int k = lane; k < NOUT; k += 32) s_acc[warp][k] = 0.0;
-  // sequence number of this sweep (the previous sweep on this problem has completed: griddepcontrol.wait above)
-  const unsigned int launch_tag = __ldcg(args.launch_seq) + 1u;
-
-  PoseConsts pc;
-  {
-    double pose[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) pose[i] = args.pose7[i];
-    make_pose_consts(pose, &pc);
+  // sequence number of the first sweep of this launch (the previous sweep on this problem has completed: griddepcontrol.wait)
+  const unsigned int launch_tag0 = __ldcg(args.launch_seq) + 1u;
+  // block 0 runs the LM update: its state is fetched now, far away from the critical tail
+  if (MODE == kModeLM && args.lm != nullptr && blockIdx.x == 0) {
+    const unsigned long long* g_core = reinterpret_cast<const unsigned long long*>(&args.lm->core);
+    for (int k = threadIdx.x; k < kLmCoreWords; k += kThreads) s_core[k] = __ldcg(g_core + k);
   }
 
+  PoseConsts pc;
   int n_tile = 0;
 
   // expands the parked pieces (one per lane) and folds them into the warp accumulator
@@ -429,6 +448,17 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     __syncwarp();
     n_tile = 0;
   };
+
+  int gc_base = 0;
+  for (int sw = 0;; ++sw) {  // one pass per sweep (exactly one unless the kernel loops the LM by itself)
+  const unsigned int launch_tag = LOOP ? launch_tag0 + (unsigned int)sw : launch_tag0;
+  for (int k = lane; k < NOUT; k += 32) s_acc[warp][k] = 0.0;
+  {
+    double pose[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) pose[i] = __ldcg(args.pose7 + i);
+    make_pose_consts(pose, &pc);
+  }
 
   // ---- main stream ----
   if (n_chunks > 0) {
@@ -491,10 +521,11 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     };
 
     for (int ch = 0; ch < n_chunks; ++ch) {
-      const int st = ch % NST;
+      const int gc = LOOP ? gc_base + ch : ch;  // running stage number -> ring slot and mbarrier phase
+      const int st = gc % NST;
       const int64_t cb = p0 + (int64_t)ch * CH;
       const int64_t ce = (cb + CH < p1) ? cb + CH : p1;
-      mbar_wait(bars + st, (uint32_t)(ch / NST) & 1u);
+      mbar_wait(bars + st, (uint32_t)(gc / NST) & 1u);
       const double* sx = ring + st * SST;
       // this lane's points of the stage: local indices 64 g + 2 lane, 64 g + 2 lane + 1 (conflict-free LDS.128)
       double2 X[G], Y[G], Z[G];
@@ -545,10 +576,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
       // every lane has consumed its registers' worth of the stage (data dependence), so the slot can be handed
       // back to the TMA engine: the other stage stays in flight meanwhile
       __syncwarp();
-      if (lane == 0 && ch + NST < n_chunks) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue_chunk(ch + NST);
-      }
+      if (issued < total_chunks) issue_one(true);
     }
     if (open) park_piece();  // the last frame continues in the next warp's range
   }
@@ -601,13 +629,15 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   // dependent ones (partials -> release ticket -> acquire poll -> partial loads).
   const unsigned long long ll_tag = (unsigned long long)launch_tag << 32;
   __syncthreads();
+  double block_sum = 0.0;
   if (threadIdx.x < NOUT) {
-    double v = 0.0;
 #pragma unroll
-    for (int wv = 0; wv < kWarps; ++wv) v += s_acc[wv][threadIdx.x];
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    st_volatile_v2(args.partials_ll + ((int64_t)blockIdx.x * kMaxOut + threadIdx.x) * 2, ll_tag | (bits & 0xffffffffull),
-                   ll_tag | (bits >> 32));
+    for (int wv = 0; wv < kWarps; ++wv) block_sum += s_acc[wv][threadIdx.x];
+    if (gridDim.x > 1) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(block_sum);
+      st_volatile_v2(args.partials_ll + ((int64_t)blockIdx.x * kMaxOut + threadIdx.x) * 2, ll_tag | (bits & 0xffffffffull),
+                     ll_tag | (bits >> 32));
+    }
   }
   CLC_STAMP(3);
   // let the next sweep's blocks be scheduled on the SMs this grid is vacating (they only prefetch until we complete)
@@ -625,7 +655,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     constexpr int NB = 10;  // blocks per thread and round
     double* s_gather = &s_red[0][0];
     static_assert(kWarps * 32 >= PARTS * NOUT, "s_red holds one value per gathering thread");
-    if (threadIdx.x < PARTS * NOUT) {
+    if (gridDim.x > 1 && threadIdx.x < PARTS * NOUT) {
       const int k = threadIdx.x % NOUT, part = threadIdx.x / NOUT;
       double acc = 0.0;
       for (int base = part; base < (int)gridDim.x; base += PARTS * NB) {
@@ -663,11 +693,14 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
       }
       s_gather[threadIdx.x] = acc;
     }
-    __syncthreads();
-    double total = 0.0;
-    if (threadIdx.x < NOUT) {
+    double total = block_sum;  // a single-block grid: nothing to gather
+    if (gridDim.x > 1) {
+      __syncthreads();
+      total = 0.0;
+      if (threadIdx.x < NOUT) {
 #pragma unroll
-      for (int part = 0; part < PARTS; ++part) total += s_gather[part * NOUT + threadIdx.x];
+        for (int part = 0; part < PARTS; ++part) total += s_gather[part * NOUT + threadIdx.x];
+      }
     }
     if (args.nranks > 1) {
       // ---- fused all-reduce: NVLink stores into every rank's mailbox, tagged words, deterministic rank-order sum ----
@@ -724,11 +757,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     CLC_STAMP(4);
     if (threadIdx.x == 0) *args.launch_seq = launch_tag;
     if (MODE == kModeLM && args.lm != nullptr) {
-      // stage the hot LM state through shared memory: one parallel round trip in, one out, instead of one per field
-      unsigned long long* s_core = reinterpret_cast<unsigned long long*>(s_dyn);  // the rings are idle by now
-      const unsigned long long* g_core = reinterpret_cast<const unsigned long long*>(&args.lm->core);
-      for (int k = threadIdx.x; k < kLmCoreWords; k += kThreads) s_core[k] = __ldcg(g_core + k);
-      __syncthreads();
+      // the hot LM state sits in shared memory since the start of the kernel: no global round trip on the serial tail
       if (threadIdx.x == 0) {
         double sums[kNumSums];
         for (int k = 0; k < kNumSums; ++k) sums[k] = s_red[0][k];
@@ -745,6 +774,15 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     }
     CLC_STAMP(5);
   }
+  // ---- next sweep of the same launch (single-block grids looping the LM in the kernel) ----
+  if (!LOOP || sw + 1 >= sweeps_max) break;
+  gc_base += n_chunks;
+  __syncthreads();  // the candidate pose written above is visible to the whole block
+  if (reinterpret_cast<const LmCore*>(s_core)->done != 0) {
+    drain(gc_base);  // stages prefetched for a sweep that will not happen
+    break;
+  }
+  }  // sweeps
 }
 
 // ---- K3: LM update as its own launch (multi-rank: runs after the all-reduce of `sums`) --------------------------
