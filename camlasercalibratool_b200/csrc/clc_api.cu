@@ -248,6 +248,7 @@ struct clc_problem {
   double* edge_pt = nullptr;
   unsigned long long* partials_ll = nullptr;  // tagged block partials (clc_kernels.cuh)
   unsigned int* launch_seq = nullptr;
+  unsigned long long* pose_ll = nullptr;      // looping grids: next pose + done flag as tagged words
   double* sums = nullptr;
   double* pose = nullptr;
   clc::LmState* lm = nullptr;
@@ -255,7 +256,8 @@ struct clc_problem {
   int64_t flush_n = 0;
   unsigned long long* timing = nullptr;  // profiling hook (clc_debug_sweep_timing)
   bool use_pdl = true;                   // CLC_PDL=0 disables programmatic dependent launch in the LM loop
-  bool loop_in_kernel = true;            // CLC_LOOP_IN_KERNEL=0: one launch per LM iteration also for single-block problems
+  int loop_in_kernel = 1;                // CLC_LOOP_IN_KERNEL: 0 one launch per LM iteration; 1 single-block problems run the whole
+                                         // LM loop in one launch; 2 every problem does (persistent grid, block 0 hands out the poses)
   // pinned host mirrors (views into one pooled block)
   PinnedBlock* pinned = nullptr;
   double* h_sums = nullptr;
@@ -313,6 +315,7 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
   a.partials_ll = p->partials_ll;
   a.sums = p->sums;
   a.launch_seq = p->launch_seq;
+  a.pose_ll = p->pose_ll;
   a.lm = d_lm;
   a.use_loss = loss ? 1 : 0;
   a.use_edges = edges ? 1 : 0;
@@ -347,10 +350,14 @@ int launch_sweep(clc_problem* p, int mode, bool loss, bool edges, const double* 
     le = p->planar ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeClosedForm, true>, v, a)
                    : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeClosedForm, false>, v, a);
   } else if (loop_sweeps > 1) {
-    // single-block problems: the instantiation that loops the LM in the kernel (never planar: those engage on large data only)
-    if (p->planar || p->grid != 1 || d_lm == nullptr) return fail(CLC_ERR_INVALID, "internal: looping sweep on a multi-block / planar problem");
-    le = loss ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, false, true>, v, a)
-              : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeLM, false, true>, v, a);
+    // the instantiations that loop the LM inside the kernel (one launch per solve)
+    if (d_lm == nullptr) return fail(CLC_ERR_INVALID, "internal: looping sweep without an LM state");
+    if (loss)
+      le = p->planar ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, true, true>, v, a)
+                     : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, false, true>, v, a);
+    else
+      le = p->planar ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeLM, true, true>, v, a)
+                     : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<false, clc::kModeLM, false, true>, v, a);
   } else if (loss) {
     le = p->planar ? cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, true>, v, a)
                    : cudaLaunchKernelEx(&cfg, clc::clc_sweep_kernel<true, clc::kModeLM, false>, v, a);
@@ -441,10 +448,9 @@ int finish_create(clc_problem* p) {
         (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, false>,         (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, true>,
         (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, false>,        (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, true>,
         (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, false>, (const void*)clc::clc_sweep_kernel<false, clc::kModeClosedForm, true>,
-        (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, false, true>,   nullptr,
-        (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, false, true>,  nullptr};
+        (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, false, true>,   (const void*)clc::clc_sweep_kernel<true, clc::kModeLM, true, true>,
+        (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, false, true>,  (const void*)clc::clc_sweep_kernel<false, clc::kModeLM, true, true>};
     for (int v = 0; v < 10; ++v) {
-      if (variants[v] == nullptr) continue;
       const void* fn = variants[v];
       const int smem = clc::dyn_smem_bytes((v & 1) != 0);  // odd entries are the planar instantiations
       CLC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -462,10 +468,12 @@ int finish_create(clc_problem* p) {
   }
   p->grid_full = p->num_sms * blocks_per_sm;
   if (const char* env = std::getenv("CLC_PDL")) p->use_pdl = std::atoi(env) != 0;
-  if (const char* env = std::getenv("CLC_LOOP_IN_KERNEL")) p->loop_in_kernel = std::atoi(env) != 0;
+  if (const char* env = std::getenv("CLC_LOOP_IN_KERNEL")) p->loop_in_kernel = std::atoi(env);
   CLC_CUDA(cudaMallocAsync(&p->sums, sizeof(double) * clc::kMaxOut, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->pose, sizeof(double) * 8, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->launch_seq, sizeof(unsigned int), p->stream));
+  CLC_CUDA(cudaMallocAsync(&p->pose_ll, sizeof(unsigned long long) * 16, p->stream));
+  CLC_CUDA(cudaMemsetAsync(p->pose_ll, 0, sizeof(unsigned long long) * 16, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->lm, sizeof(clc::LmState), p->stream));
   CLC_CUDA(cudaMallocAsync(&p->p2p_error, sizeof(int), p->stream));
   CLC_CUDA(cudaMemsetAsync(p->p2p_error, 0, sizeof(int), p->stream));
@@ -626,7 +634,7 @@ int clc_problem_destroy(clc_problem* p) {
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->stream) {
     void* bufs[] = {p->x, p->y, p->z, p->d_nonplanar, p->frame_pose, p->frame_pose_true, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
-                    p->partials_ll, p->sums, p->pose, p->launch_seq, p->lm, p->flush_buf, p->p2p_error};
+                    p->partials_ll, p->sums, p->pose, p->launch_seq, p->pose_ll, p->lm, p->flush_buf, p->p2p_error};
     for (void* b : bufs)
       if (b) cudaFreeAsync(b, p->stream);  // back to the device's memory pool: re-creating a problem is cheap
     cudaStreamSynchronize(p->stream);
@@ -1171,10 +1179,16 @@ int solve_all(clc_problem* const* ps, int n, double pose7[7], const clc_lm_optio
   if (rc != CLC_OK) return rc;
   const int max_sweeps = ctx[0].max_sweeps;
   int launched = 0;
-  if (n == 1 && ps[0]->grid == 1 && ctx[0].fused_update && ps[0]->nranks <= 1 && ps[0]->loop_in_kernel) {
-    // a problem that fits one block: ONE launch runs the whole LM loop (sweep, reduce, lm_update, next sweep)
-    rc = solve_launch_one(ps[0], &ctx[0], max_sweeps);
-    if (rc != CLC_OK) return rc;
+  bool loop_launch = true;
+  for (int g = 0; g < n; ++g)
+    loop_launch = loop_launch && ctx[g].fused_update &&
+                  (ps[g]->loop_in_kernel >= 2 || (ps[g]->loop_in_kernel == 1 && ps[g]->grid == 1 && ps[g]->nranks <= 1));
+  if (loop_launch) {
+    // ONE launch per device runs the whole LM loop (sweep, reduce, [peer exchange,] lm_update, next sweep)
+    for (int g = 0; g < n; ++g) {
+      rc = solve_launch_one(ps[g], &ctx[g], max_sweeps);
+      if (rc != CLC_OK) return rc;
+    }
     launched = max_sweeps;
   }
   while (launched < max_sweeps) {
@@ -1252,17 +1266,57 @@ int clc_problem_line_fit(clc_problem* p, double* lines, int max_num_iterations, 
   return CLC_OK;
 }
 
+// One scan per call, as the reference calls it (main/calibr_offline.cpp:124, a few hundred points): no problem object, no
+// layout kernels -- a per-thread cache of one stream, one device buffer and one pinned scratch, three driver calls and a
+// one-warp kernel on the scan's own AoS array.
+namespace {
+struct LineFitCache {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  double* d_pts = nullptr;   // [capacity * 3] + 2 (the line)
+  int64_t capacity = 0;
+  double* h_line = nullptr;  // pinned, 2 doubles
+  ~LineFitCache() {
+    if (device < 0) return;
+    // no CUDA calls at thread exit: the context may already be gone; the few KB are reclaimed with the process
+  }
+};
+thread_local LineFitCache g_line_cache;
+}  // namespace
+
 int clc_line_fit_points(const double* points_xyz, int64_t n, double line[2], int max_num_iterations) {
-  if (!points_xyz || n < 0 || !line) return fail(CLC_ERR_INVALID, "bad line-fit arguments");
-  const double pose[7] = {0, 0, 0, 1, 0, 0, 0};
-  const int64_t off[2] = {0, n};
-  clc_problem_desc d = {1, pose, off, points_xyz, nullptr, 1, 0.05, -1};  // CauchyLoss(0.05), reference :416
-  clc_problem* p = nullptr;
-  int rc = clc_problem_create(&p, &d);
-  if (rc != CLC_OK) return rc;
-  rc = clc_problem_line_fit(p, line, max_num_iterations, nullptr);
-  clc_problem_destroy(p);
-  return rc;
+  if (!points_xyz || n < 0 || !line || max_num_iterations < 0) return fail(CLC_ERR_INVALID, "bad line-fit arguments");
+  LineFitCache& c = g_line_cache;
+  int device = 0;
+  CLC_CUDA(cudaGetDevice(&device));
+  if (c.device != device) {
+    int major = 0;
+    CLC_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major < 10) return fail(CLC_ERR_CUDA, "libclc_b200 is built for sm_100a only");
+    if (c.stream) { cudaStreamDestroy(c.stream); c.stream = nullptr; }
+    if (c.d_pts) { cudaFree(c.d_pts); c.d_pts = nullptr; c.capacity = 0; }
+    CLC_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (!c.h_line) CLC_CUDA(cudaMallocHost(&c.h_line, 2 * sizeof(double)));
+    c.device = device;
+  }
+  if (n > c.capacity) {
+    if (c.d_pts) CLC_CUDA(cudaFree(c.d_pts));
+    c.d_pts = nullptr;
+    c.capacity = std::max<int64_t>(2 * n, 4096);
+    CLC_CUDA(cudaMalloc(&c.d_pts, sizeof(double) * (3 * (size_t)c.capacity + 2)));
+  }
+  double* d_line = c.d_pts + 3 * c.capacity;
+  c.h_line[0] = line[0];
+  c.h_line[1] = line[1];
+  if (n > 0) CLC_CUDA(cudaMemcpyAsync(c.d_pts, points_xyz, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c.stream));
+  CLC_CUDA(cudaMemcpyAsync(d_line, c.h_line, 2 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  clc::clc_line_fit_single_kernel<<<1, 32, 0, c.stream>>>(c.d_pts, n, max_num_iterations, 0.05, d_line);  // CauchyLoss(0.05), reference :416
+  CLC_LAUNCH_CHECK();
+  CLC_CUDA(cudaMemcpyAsync(c.h_line, d_line, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  CLC_CUDA(cudaStreamSynchronize(c.stream));
+  line[0] = c.h_line[0];
+  line[1] = c.h_line[1];
+  return CLC_OK;
 }
 
 int clc_scan_segments(const float* ranges, int64_t n_scans, int64_t n_beams, double angle_min, double angle_increment,

@@ -89,8 +89,10 @@ struct SweepArgs {
   LmState* lm;                // non-null: the last block also runs lm_update (single-rank fused mode)
   int use_loss;
   int use_edges;
-  int loop_sweeps;            // > 1 (single-block grids with a fused LM update only): the kernel runs up to that many LM
+  int loop_sweeps;            // > 1 (LOOP instantiations with a fused LM update only): the kernel runs up to that many LM
                               // iterations by itself -- sweep, reduce, lm_update, next sweep -- instead of one per launch
+  unsigned long long* pose_ll;  // [16] looping multi-block grids: block 0 hands the next pose (7 doubles) and the `done` flag to
+                                // the other blocks as tagged words (same protocol as partials_ll)
   unsigned long long* timing;  // optional [gridDim.x * 8] globaltimer stamps (profiling hook), nullptr normally;
                                // followed by [gridDim.x * kWarps] per-warp "stream done" stamps
   // fused all-reduce over NVLink peer memory (nranks > 1): every rank's last block stores its sums into every rank's
@@ -309,6 +311,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   __shared__ double s_acc[kWarps][NOUT];
   __shared__ double s_red[kWarps][32];
   __shared__ unsigned long long s_core[kLmCoreWords];  // block 0: the hot LM state
+  __shared__ double s_next[8];                           // looping grids: pose of the next sweep + the `done` flag
 
   CLC_STAMP(0);
   if (args.timing != nullptr && threadIdx.x == 0) {
@@ -340,7 +343,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   };
   // Stage slots and mbarrier phases follow a running count of issued stages (`issued`, kept by every lane), so that a kernel
   // that loops over several sweeps (loop_sweeps > 1) keeps prefetching across the reduce + LM update between two sweeps.
-  const int sweeps_max = (LOOP && args.loop_sweeps > 1 && gridDim.x == 1 && MODE == kModeLM && args.lm != nullptr) ? args.loop_sweeps : 1;
+  const int sweeps_max = (LOOP && args.loop_sweeps > 1 && MODE == kModeLM && args.lm != nullptr) ? args.loop_sweeps : 1;
   const int total_chunks = LOOP ? sweeps_max * n_chunks : n_chunks;
   int issued = 0, next_c = 0;  // next_c == issued mod n_chunks
   auto issue_one = [&](bool slot_was_read) {
@@ -398,7 +401,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   }
 
   // sequence number of the first sweep of this launch (the previous sweep on this problem has completed: griddepcontrol.wait)
-  const unsigned int launch_tag0 = __ldcg(args.launch_seq) + 1u;
+  const unsigned int launch_tag0 = *args.launch_seq + 1u;  // (plain load: one L2 request per SM, see the pose below)
   // block 0 runs the LM update: its state is fetched now, far away from the critical tail
   if (MODE == kModeLM && args.lm != nullptr && blockIdx.x == 0) {
     const unsigned long long* g_core = reinterpret_cast<const unsigned long long*>(&args.lm->core);
@@ -456,7 +459,9 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   {
     double pose[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) pose[i] = __ldcg(args.pose7 + i);
+    // plain (L1-cached) loads: 2368 warps read the same 56 bytes -- one L2 request per SM instead of one per warp (L1 is
+    // invalidated at every kernel launch, so the pose written by the previous sweep's block 0 is what arrives)
+    for (int i = 0; i < 7; ++i) pose[i] = (LOOP && sw > 0) ? s_next[i] : args.pose7[i];
     make_pose_consts(pose, &pc);
   }
 
@@ -645,10 +650,10 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   // The final reduction (and the LM update) always runs on block 0 -- the persistent grid is fully co-resident, so
   // block 0 can wait for the other blocks -- rather than on whichever block happens to finish last: the ~1000 instructions
   // of that serial tail then stay warm in ONE SM's instruction cache from launch to launch.
-  if (blockIdx.x != 0) return;
+  if (blockIdx.x != 0 && (!LOOP || sweeps_max == 1)) return;
 
   // ---- block 0: deterministic sum of the block partials ----
-  {
+  if (blockIdx.x == 0) {
     // thread (part, k) polls the words of output k of blocks part, part + PARTS, ... (all its loads in flight at once)
     // and adds them in block order; the PARTS partial results are then added in part order: a fixed tree.
     constexpr int PARTS = kThreads / NOUT;
@@ -707,7 +712,9 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
       // the sequence number lives on the device: sweeps that no-op (LM already finished) must not consume one, or two
       // consecutive real exchanges could land in the same parity slot while a slow peer is still reading it
       double* s_tot = s_acc[0];                                 // [NOUT] this rank's totals
-      double* s_x = reinterpret_cast<double*>(s_dyn);           // [nranks][NOUT] (the rings are idle by now)
+      double* s_x = reinterpret_cast<double*>(s_dyn) + kWarps * RING;  // [nranks][NOUT] in the tiles, idle between two sweeps
+                                                                       // (not the rings: a looping grid is prefetching into them)
+      static_assert(kWarps * kTileDoublesPerWarp >= kMaxRanks * kMaxOut, "the tiles hold one value per rank and output");
       __syncthreads();                                          // s_gather reads are done before s_acc/s_dyn are reused
       if (threadIdx.x < NOUT) s_tot[threadIdx.x] = total;
       __syncthreads();
@@ -769,16 +776,47 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
         }
       }
       __syncthreads();
+      if (LOOP && sweeps_max > 1 && threadIdx.x < 8) {
+        // the next pose and the `done` flag: to this block through shared memory, to the other blocks as tagged words
+        const LmCore* core = reinterpret_cast<const LmCore*>(s_core);
+        const double v = threadIdx.x < 7 ? core->cand[threadIdx.x] : (double)core->done;
+        s_next[threadIdx.x] = v;
+        if (gridDim.x > 1) {
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+          st_volatile_v2(args.pose_ll + 2 * threadIdx.x, ll_tag | (bits & 0xffffffffull), ll_tag | (bits >> 32));
+        }
+      }
       unsigned long long* o_core = reinterpret_cast<unsigned long long*>(&args.lm->core);
       for (int k = threadIdx.x; k < kLmCoreWords; k += kThreads) o_core[k] = s_core[k];
     }
     CLC_STAMP(5);
+  } else {
+    // ---- looping grid, blocks other than 0: wait for the next pose from block 0 ----
+    if (threadIdx.x < 8 && sw + 1 < sweeps_max) {
+      unsigned long long a0, a1, t0 = 0;
+      unsigned int polls = 0;
+      for (;;) {
+        ld_volatile_v2(args.pose_ll + 2 * threadIdx.x, a0, a1);
+        if ((a0 & 0xffffffff00000000ull) == ll_tag && (a1 & 0xffffffff00000000ull) == ll_tag) break;
+        if ((++polls & 0xffu) == 0u) {
+          const unsigned long long now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > 10000000000ull) {  // 10 s without a pose: block 0 is gone -- stop instead of hanging
+            if (args.error != nullptr) *args.error = 2;
+            a0 = a1 = 0;
+            break;
+          }
+        }
+      }
+      const bool lost = (a0 | a1) == 0ull;
+      s_next[threadIdx.x] = lost ? (double)CLC_TERM_FAILURE : __longlong_as_double((long long)((a1 << 32) | (a0 & 0xffffffffull)));
+    }
   }
-  // ---- next sweep of the same launch (single-block grids looping the LM in the kernel) ----
+  // ---- next sweep of the same launch (LOOP instantiations: the LM runs inside the kernel) ----
   if (!LOOP || sw + 1 >= sweeps_max) break;
   gc_base += n_chunks;
-  __syncthreads();  // the candidate pose written above is visible to the whole block
-  if (reinterpret_cast<const LmCore*>(s_core)->done != 0) {
+  __syncthreads();  // s_next is visible to the whole block
+  if (s_next[7] != 0.0) {
     drain(gc_base);  // stages prefetched for a sweep that will not happen
     break;
   }

@@ -223,24 +223,22 @@ __global__ void clc_scan_segments_kernel(const float* __restrict__ ranges, int64
   seg_end[s] = b;
 }
 
-// lines[f*2..+2]: start value in, fitted line out; info[f*4..+4] (optional): termination, iterations, sweeps, final cost
-__global__ void __launch_bounds__(256) clc_line_fit_kernel(const double* __restrict__ x, const double* __restrict__ y,
-                                                          const int64_t* __restrict__ offsets, int64_t n_frames,
-                                                          int max_num_iterations, double cauchy_a,
-                                                          double* __restrict__ lines, double* __restrict__ info) {
+// One warp fits one scan: points i in [b, e) at x[i * stride], y[i * stride] (stride 1: the SoA arrays of a problem; stride 3:
+// the AoS xyz array of a std::vector<Eigen::Vector3d>).  line: start value in, fitted line out; info (optional, 4 doubles):
+// termination, iterations, sweeps, final cost.
+__device__ __forceinline__ void line_fit_warp(const double* __restrict__ x, const double* __restrict__ y, int stride, int64_t b,
+                                              int64_t e, int max_num_iterations, double cauchy_a, double* __restrict__ line,
+                                              double* __restrict__ info) {
   const int lane = threadIdx.x & 31;
-  const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (f >= n_frames) return;
-  const int64_t b = offsets[f], e = offsets[f + 1];
   Lm2 s;
-  lm2_init(s, lines[2 * f], lines[2 * f + 1]);
+  lm2_init(s, line[0], line[1]);
   const double inv_a2 = 1.0 / (cauchy_a * cauchy_a), a2 = cauchy_a * cauchy_a;
   while (!s.done) {
     const double m0 = s.cand[0], m1 = s.cand[1];
     double hxx = 0.0, hxy = 0.0, hyy = 0.0, gx = 0.0, gy = 0.0, prod = 1.0;
     int esum = 0;
     for (int64_t i = b + lane; i < e; i += 32) {
-      const double px = x[i], py = y[i];
+      const double px = x[i * stride], py = y[i * stride];
       const double r = fma(m0, px, fma(m1, py, 1.0));
       const double u = fma(r * inv_a2, r, 1.0);
       const double w = 1.0 / u;
@@ -268,15 +266,33 @@ __global__ void __launch_bounds__(256) clc_line_fit_kernel(const double* __restr
     lm2_update(s, sums, max_num_iterations);
   }
   if (lane == 0) {
-    lines[2 * f] = s.x[0];
-    lines[2 * f + 1] = s.x[1];
+    line[0] = s.x[0];
+    line[1] = s.x[1];
     if (info != nullptr) {
-      info[4 * f] = (double)s.done;
-      info[4 * f + 1] = (double)s.iteration;
-      info[4 * f + 2] = (double)s.sweeps;
-      info[4 * f + 3] = s.x_cost;
+      info[0] = (double)s.done;
+      info[1] = (double)s.iteration;
+      info[2] = (double)s.sweeps;
+      info[3] = s.x_cost;
     }
   }
+}
+
+// batched: one warp per frame of a device-resident problem; lines[f*2..+2], info[f*4..+4]
+__global__ void __launch_bounds__(256) clc_line_fit_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                          const int64_t* __restrict__ offsets, int64_t n_frames,
+                                                          int max_num_iterations, double cauchy_a,
+                                                          double* __restrict__ lines, double* __restrict__ info) {
+  const int64_t f = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= n_frames) return;
+  line_fit_warp(x, y, 1, offsets[f], offsets[f + 1], max_num_iterations, cauchy_a, lines + 2 * f,
+                info != nullptr ? info + 4 * f : nullptr);
+}
+
+// one scan straight from its AoS xyz array (the per-call shape of the reference's LineFittingCeres, main/calibr_offline.cpp:124):
+// one warp, no problem object
+__global__ void __launch_bounds__(32) clc_line_fit_single_kernel(const double* __restrict__ pts_xyz, int64_t n, int max_num_iterations,
+                                                                double cauchy_a, double* __restrict__ line) {
+  line_fit_warp(pts_xyz, pts_xyz + 1, 3, 0, n, max_num_iterations, cauchy_a, line, nullptr);
 }
 #endif
 
