@@ -51,6 +51,14 @@ constexpr int kPlanarStages = CLC_PLANAR_STAGES;
 constexpr int kPlanarChunk = CLC_PLANAR_CHUNK;
 static_assert(kChunk % 64 == 0 && kPlanarChunk % 64 == 0, "stages are made of 64-point groups");
 constexpr int kMaxChunk = kChunk > kPlanarChunk ? kChunk : kPlanarChunk;
+// Soft lockstep of the warps of a block: a warp does not start stage c before every warp of its block has finished stage
+// c - kLockstepSlack (0 = off).  The issue arbiter lets some warps run ahead; they then leave early and the block finishes
+// its last stages with few loads in flight.  Holding the front-runners back hands their issue slots to the stragglers: the
+// block's warps end together, at the block's mean finishing time, with the static (deterministic) partition untouched.
+#ifndef CLC_LOCKSTEP_SLACK
+#define CLC_LOCKSTEP_SLACK 0
+#endif
+constexpr int kLockstepSlack = CLC_LOCKSTEP_SLACK;
 constexpr int kBarsPerWarp = kStages > kPlanarStages ? kStages : kPlanarStages;
 constexpr int kTileDoublesPerWarp = 32 * kTileStride;
 // dynamic shared memory of a kernel family: per-warp ring + per-warp tile + per-warp mbarriers
@@ -312,6 +320,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   __shared__ double s_red[kWarps][32];
   __shared__ unsigned long long s_core[kLmCoreWords];  // block 0: the hot LM state
   __shared__ double s_next[8];                           // looping grids: pose of the next sweep + the `done` flag
+  __shared__ int s_prog[32];                             // stages finished by every warp (soft lockstep)
 
   CLC_STAMP(0);
   if (args.timing != nullptr && threadIdx.x == 0) {
@@ -466,6 +475,11 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   }
 
   // ---- main stream ----
+  if (kLockstepSlack > 0) {
+    if (lane == 0) s_prog[warp] = n_chunks > 0 ? 0 : 0x7fffffff;
+    if (warp == 0 && lane >= kWarps) s_prog[lane] = 0x7fffffff;
+    __syncthreads();
+  }
   if (n_chunks > 0) {
     int64_t f = pv.warp_first_frame[gwarp];
     int64_t f_end = pv.offsets[f + 1];
@@ -530,6 +544,9 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
       const int st = gc % NST;
       const int64_t cb = p0 + (int64_t)ch * CH;
       const int64_t ce = (cb + CH < p1) ? cb + CH : p1;
+      if (kLockstepSlack > 0) {
+        while (__reduce_min_sync(0xffffffffu, *(volatile int*)&s_prog[lane]) < ch - kLockstepSlack) __nanosleep(40);
+      }
       mbar_wait(bars + st, (uint32_t)(gc / NST) & 1u);
       const double* sx = ring + st * SST;
       // this lane's points of the stage: local indices 64 g + 2 lane, 64 g + 2 lane + 1 (conflict-free LDS.128)
@@ -582,6 +599,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
       // back to the TMA engine: the other stage stays in flight meanwhile
       __syncwarp();
       if (issued < total_chunks) issue_one(true);
+      if (kLockstepSlack > 0 && lane == 0) *(volatile int*)&s_prog[warp] = (ch + 1 == n_chunks) ? 0x7fffffff : ch + 1;
     }
     if (open) park_piece();  // the last frame continues in the next warp's range
   }

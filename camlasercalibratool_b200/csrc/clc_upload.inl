@@ -107,7 +107,12 @@ struct PinnedSlots {
     }
     while ((int)slots.size() < n) {
       void* s = nullptr;
-      CLC_CUDA(cudaHostAlloc(&s, slot_bytes, cudaHostAllocPortable));
+      // CLC_UPLOAD_WC=1: write-combined pinned slots (the packers only ever write them, with non-temporal stores, and the DMA
+      // engine reads them without snooping the CPU caches)
+      unsigned flags = cudaHostAllocPortable;
+      if (const char* env = std::getenv("CLC_UPLOAD_WC"))
+        if (std::atoi(env) != 0) flags |= cudaHostAllocWriteCombined;
+      CLC_CUDA(cudaHostAlloc(&s, slot_bytes, flags));
       slots.push_back(s);
     }
     return CLC_OK;
