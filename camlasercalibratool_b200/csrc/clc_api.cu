@@ -238,7 +238,8 @@ struct clc_problem {
   int use_loss = 1;
   double cauchy_a = 0.05;
   // device buffers
-  double *x = nullptr, *y = nullptr, *z = nullptr;
+  double *x = nullptr, *y = nullptr, *z = nullptr;  // views into xy_block / z_block
+  void *xy_block = nullptr, *z_block = nullptr;     // the allocations (x and y share one; z is created only when needed)
   double* frame_pose = nullptr;
   double* frame_pose_true = nullptr;  // synthetic problems with a camera model: the poses the points were generated from
   double* plane = nullptr;
@@ -500,8 +501,9 @@ int finish_create(clc_problem* p) {
   p->planar = p->z_all_zero && p->planar_mode != 0 && p->n_points >= p->planar_min_points;
   if (p->planar && p->z != nullptr) {
     // a third of the point storage goes back to the pool
-    CLC_CUDA(cudaFreeAsync(p->z, p->stream));
+    CLC_CUDA(cudaFreeAsync(p->z_block, p->stream));
     p->z = nullptr;
+    p->z_block = nullptr;
   } else if (!p->planar) {
     int rc = materialise_z(p);
     if (rc != CLC_OK) return rc;
@@ -548,12 +550,39 @@ int init_device(clc_problem* p, int device) {
   return CLC_OK;
 }
 
+// Placement of the coordinate arrays relative to each other (experiment knobs CLC_SKEW_Y / CLC_SKEW_Z, bytes): x and y live
+// in one allocation, y starting skew_y bytes after the end of x; z is its own allocation (it exists only for non-planar data)
+// whose start is shifted so that (z - x) mod 2 MiB == skew_z.
+int64_t env_skew(const char* name, int64_t dflt) {
+  const char* env = std::getenv(name);
+  if (!env) return dflt;
+  const int64_t v = std::atoll(env);
+  return v < 0 ? 0 : (v / 512) * 512;  // bulk copies want 16-byte alignment; keep whole 512-byte units
+}
+constexpr int64_t kSkewPeriod = (int64_t)2 << 20;
+
+int alloc_z(clc_problem* p) {
+  const size_t bytes = sizeof(double) * (size_t)p->n_points_padded;
+  CLC_CUDA(cudaMallocAsync(&p->z_block, bytes + (size_t)kSkewPeriod, p->stream));
+  const int64_t want = env_skew("CLC_SKEW_Z", 0) % kSkewPeriod;
+  const int64_t have = (int64_t)((reinterpret_cast<uintptr_t>(p->z_block) - reinterpret_cast<uintptr_t>(p->x)) % (uintptr_t)kSkewPeriod);
+  const int64_t shift = ((want - have) % kSkewPeriod + kSkewPeriod) % kSkewPeriod;
+  p->z = reinterpret_cast<double*>(static_cast<char*>(p->z_block) + shift);
+  if (std::getenv("CLC_DEBUG_LAYOUT")) std::fprintf(stderr, "CLC_DEBUG_LAYOUT x=%p y=%p z=%p (z block %p)\n", (void*)p->x, (void*)p->y, (void*)p->z, p->z_block);
+  return CLC_OK;
+}
+
 int alloc_points(clc_problem* p, bool with_z) {
   p->n_points_padded = round_up(p->n_points, clc::kMaxChunk) + clc::kMaxChunk;
   const size_t bytes = sizeof(double) * (size_t)p->n_points_padded;
-  CLC_CUDA(cudaMallocAsync(&p->x, bytes, p->stream));
-  CLC_CUDA(cudaMallocAsync(&p->y, bytes, p->stream));
-  if (with_z) CLC_CUDA(cudaMallocAsync(&p->z, bytes, p->stream));
+  const int64_t skew_y = env_skew("CLC_SKEW_Y", 0);
+  CLC_CUDA(cudaMallocAsync(&p->xy_block, 2 * bytes + (size_t)skew_y, p->stream));
+  p->x = static_cast<double*>(p->xy_block);
+  p->y = reinterpret_cast<double*>(static_cast<char*>(p->xy_block) + bytes + skew_y);
+  if (with_z) {
+    int rc = alloc_z(p);
+    if (rc != CLC_OK) return rc;
+  }
   CLC_CUDA(cudaMallocAsync(&p->d_nonplanar, sizeof(int), p->stream));
   CLC_CUDA(cudaMemsetAsync(p->d_nonplanar, 0, sizeof(int), p->stream));
   // zero the padding (finite values are required beyond the last point)
@@ -567,9 +596,9 @@ int alloc_points(clc_problem* p, bool with_z) {
 // all-zero z stream for the general kernels on planar data (clc_problem_set_planar_mode(p, 0))
 int materialise_z(clc_problem* p) {
   if (p->z != nullptr) return CLC_OK;
-  const size_t bytes = sizeof(double) * (size_t)p->n_points_padded;
-  CLC_CUDA(cudaMallocAsync(&p->z, bytes, p->stream));
-  CLC_CUDA(cudaMemsetAsync(p->z, 0, bytes, p->stream));
+  int rc = alloc_z(p);
+  if (rc != CLC_OK) return rc;
+  CLC_CUDA(cudaMemsetAsync(p->z, 0, sizeof(double) * (size_t)p->n_points_padded, p->stream));
   return CLC_OK;
 }
 
@@ -633,7 +662,7 @@ int clc_problem_destroy(clc_problem* p) {
   cudaSetDevice(p->device);
   if (p->stream) cudaStreamSynchronize(p->stream);
   if (p->stream) {
-    void* bufs[] = {p->x, p->y, p->z, p->d_nonplanar, p->frame_pose, p->frame_pose_true, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
+    void* bufs[] = {p->xy_block, p->z_block, p->d_nonplanar, p->frame_pose, p->frame_pose_true, p->plane, p->offsets, p->warp_first_frame, p->edge_plane, p->edge_pt,
                     p->partials_ll, p->sums, p->pose, p->launch_seq, p->pose_ll, p->lm, p->flush_buf, p->p2p_error};
     for (void* b : bufs)
       if (b) cudaFreeAsync(b, p->stream);  // back to the device's memory pool: re-creating a problem is cheap
