@@ -409,8 +409,7 @@ int partition(clc_problem* p) {
     if (p->n_points <= single_block_max) p->grid = 1;
   }
   const int64_t n_warps = (int64_t)p->grid * clc::kWarps;
-  // ranges in 64-point units (not whole stages): every warp of the grid gets work, the last stage of a range may be short
-  p->per_warp = std::max<int64_t>(64, round_up((p->n_points + n_warps - 1) / n_warps, 64));
+  p->per_warp = std::max<int64_t>(chunk, round_up((p->n_points + n_warps - 1) / n_warps, chunk));  // whole stages
   if (p->warp_first_frame) CLC_CUDA(cudaFreeAsync(p->warp_first_frame, p->stream));
   if (p->partials_ll) CLC_CUDA(cudaFreeAsync(p->partials_ll, p->stream));
   p->warp_first_frame = nullptr;
@@ -550,9 +549,12 @@ int init_device(clc_problem* p, int device) {
   return CLC_OK;
 }
 
-// Placement of the coordinate arrays relative to each other (experiment knobs CLC_SKEW_Y / CLC_SKEW_Z, bytes): x and y live
-// in one allocation, y starting skew_y bytes after the end of x; z is its own allocation (it exists only for non-planar data)
-// whose start is shifted so that (z - x) mod 2 MiB == skew_z.
+// Placement of the coordinate arrays relative to each other.  Measured at BASELINE configs[2] (profiles/r2_layout_ab.txt):
+// the sweep kernel streams fastest when x, y and z start at the same offset within a 2 MiB page, so that a warp's three
+// bulk copies of one stage cross page boundaries together; any other relative shift that was tried costs 3-8 %.  x and y
+// live in one allocation, y starting skew_y bytes after the end of x (default: up to the next address congruent to x mod
+// 2 MiB; small problems are packed); z is its own allocation (it exists only for non-planar data) whose start is shifted so
+// that (z - x) mod 2 MiB == skew_z (default 0).  CLC_SKEW_Y / CLC_SKEW_Z (bytes) override both: the experiment knobs.
 int64_t env_skew(const char* name, int64_t dflt) {
   const char* env = std::getenv(name);
   if (!env) return dflt;
@@ -575,7 +577,8 @@ int alloc_z(clc_problem* p) {
 int alloc_points(clc_problem* p, bool with_z) {
   p->n_points_padded = round_up(p->n_points, clc::kMaxChunk) + clc::kMaxChunk;
   const size_t bytes = sizeof(double) * (size_t)p->n_points_padded;
-  const int64_t skew_y = env_skew("CLC_SKEW_Y", 0);
+  const int64_t congruent = (kSkewPeriod - (int64_t)(bytes % (size_t)kSkewPeriod)) % kSkewPeriod;
+  const int64_t skew_y = env_skew("CLC_SKEW_Y", bytes >= (size_t)(4 * kSkewPeriod) ? congruent : 0);
   CLC_CUDA(cudaMallocAsync(&p->xy_block, 2 * bytes + (size_t)skew_y, p->stream));
   p->x = static_cast<double*>(p->xy_block);
   p->y = reinterpret_cast<double*>(static_cast<char*>(p->xy_block) + bytes + skew_y);

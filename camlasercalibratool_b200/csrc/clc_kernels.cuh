@@ -82,7 +82,7 @@ struct ProblemView {
   int64_t n_frames;
   int64_t n_points;
   int64_t n_edges;            // 2 * n_frames or 0
-  int64_t per_warp;           // points per warp (multiple of 64)
+  int64_t per_warp;           // points per warp (multiple of the kernel family's stage size)
   double inv_a2;              // 1 / cauchy_a^2
   double a2;                  // cauchy_a^2
 };
@@ -344,12 +344,6 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
   double* tile = reinterpret_cast<double*>(s_dyn) + kWarps * RING + warp * kTileDoublesPerWarp;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_dyn + (size_t)kWarps * (RING + kTileDoublesPerWarp) * 8) + warp * kBarsPerWarp;
 
-  // points of stage c: full stages except possibly the last one of the range, which is cut to whole 64-point groups (the
-  // ranges are handed out in 64-point units so that every warp of the grid gets work; the arrays are zero padded)
-  auto chunk_len = [&](int c) -> int {
-    const int64_t left = p1 - (p0 + (int64_t)c * CH);
-    return left >= CH ? CH : (int)((left + 63) & ~(int64_t)63);
-  };
   // Stage slots and mbarrier phases follow a running count of issued stages (`issued`, kept by every lane), so that a kernel
   // that loops over several sweeps (loop_sweeps > 1) keeps prefetching across the reduce + LM update between two sweeps.
   const int sweeps_max = (LOOP && args.loop_sweeps > 1 && MODE == kModeLM && args.lm != nullptr) ? args.loop_sweeps : 1;
@@ -359,13 +353,14 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     if (lane == 0) {
       const int c = LOOP ? next_c : issued, st = issued % NST;
       double* dst = ring + st * SST;
-      const int64_t src = p0 + (int64_t)c * CH;  // multiple of 64 points -> 512 B aligned
-      const int len = chunk_len(c);
+      // always a whole stage (the arrays are zero padded beyond the last point; the ranges are whole stages): measured, a
+      // short last stage in 64-point units costs more than the idle warps it saves (profiles/r2_variant_sweep.txt)
+      const int64_t src = p0 + (int64_t)c * CH;  // multiple of the stage size -> 1 KiB aligned
       if (slot_was_read) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(bars + st, (PLANAR ? 2 : 3) * len * 8);
-      bulk_g2s(dst, pv.x + src, len * 8, bars + st);
-      bulk_g2s(dst + CH, pv.y + src, len * 8, bars + st);
-      if (!PLANAR) bulk_g2s(dst + 2 * CH, pv.z + src, len * 8, bars + st);
+      mbar_expect_tx(bars + st, (PLANAR ? 2 : 3) * CH * 8);
+      bulk_g2s(dst, pv.x + src, CH * 8, bars + st);
+      bulk_g2s(dst + CH, pv.y + src, CH * 8, bars + st);
+      if (!PLANAR) bulk_g2s(dst + 2 * CH, pv.z + src, CH * 8, bars + st);
     }
     ++issued;
     if (LOOP && ++next_c == n_chunks) next_c = 0;
@@ -382,21 +377,7 @@ clc_sweep_kernel(ProblemView pv, SweepArgs args) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
-  for (int g = 0; g < NST && g < total_chunks; ++g) {
-    // A short last stage that is the first thing ever copied into its ring slot: the lanes beyond it are masked out of every
-    // sum, but they are still multiplied by a zero weight -- give them finite values (in longer ranges the slot holds the
-    // points of an earlier stage).
-    const int len = chunk_len(LOOP ? next_c : issued);
-    if (len < CH) {
-      double* dst = ring + g * SST;
-      for (int i = len + lane; i < CH; i += 32) {
-        dst[i] = 0.0;
-        dst[CH + i] = 0.0;
-        if (!PLANAR) dst[2 * CH + i] = 0.0;
-      }
-    }
-    issue_one(false);
-  }
+  for (int g = 0; g < NST && g < total_chunks; ++g) issue_one(false);
   __syncwarp();
 
   // Programmatic dependent launch: everything above touched only constant data (the points), so it overlaps the
