@@ -1648,9 +1648,47 @@ int comms_create_local(std::vector<clc_comm*>* out, const int* devices, int n) {
   return CLC_OK;
 }
 
+// The mailboxes of an in-process group outlive the group: cudaMalloc / cudaFree / enabling peer access cost milliseconds,
+// and the drop-in builds a group per CamLaserCalibration() call.  One idle set per device list is kept; the exchange's
+// sequence counter lives in the mailbox block and simply keeps counting across groups.
+std::mutex g_comm_cache_mutex;
+std::vector<std::pair<std::vector<int>, std::vector<clc_comm*>>> g_comm_cache;
+
+int comms_acquire_local(std::vector<clc_comm*>* out, const int* devices, int n) {
+  const std::vector<int> key(devices, devices + n);
+  {
+    std::lock_guard<std::mutex> lock(g_comm_cache_mutex);
+    for (size_t i = 0; i < g_comm_cache.size(); ++i)
+      if (g_comm_cache[i].first == key) {
+        *out = g_comm_cache[i].second;
+        g_comm_cache.erase(g_comm_cache.begin() + (long)i);
+        return CLC_OK;
+      }
+  }
+  return comms_create_local(out, devices, n);
+}
+
+void comms_release_local(std::vector<clc_comm*>& comms) {
+  if (comms.empty()) return;
+  std::vector<int> key;
+  for (clc_comm* c : comms) key.push_back(c->device);
+  {
+    std::lock_guard<std::mutex> lock(g_comm_cache_mutex);
+    bool have = false;
+    for (auto& e : g_comm_cache) have = have || e.first == key;
+    if (!have && g_comm_cache.size() < 8) {
+      g_comm_cache.emplace_back(key, comms);
+      comms.clear();
+      return;
+    }
+  }
+  for (clc_comm* c : comms) clc_comm_destroy(c);
+  comms.clear();
+}
+
 int group_attach(clc_group* g, const int* devices, int n) {
   if (n <= 1) return CLC_OK;
-  int rc = comms_create_local(&g->comms, devices, n);
+  int rc = comms_acquire_local(&g->comms, devices, n);
   if (rc != CLC_OK) return rc;
   for (int i = 0; i < n; ++i) {
     rc = clc_problem_attach_comm(g->problems[i], g->comms[i]);
@@ -1680,7 +1718,17 @@ int resolve_devices(const int* devices, int n_devices, std::vector<int>* out) {
 
 int clc_group_destroy(clc_group* g) {
   if (!g) return CLC_OK;
+  bool clean = true;  // a group whose exchange timed out must not hand its mailboxes to the next one
+  for (clc_problem* p : g->problems) {
+    int err = 0;
+    if (p->p2p_error && cudaSetDevice(p->device) == cudaSuccess && cudaStreamSynchronize(p->stream) == cudaSuccess &&
+        cudaMemcpy(&err, p->p2p_error, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess)
+      clean = clean && err == 0;
+    else
+      clean = false;
+  }
   for (clc_problem* p : g->problems) clc_problem_destroy(p);
+  if (clean) comms_release_local(g->comms);
   for (clc_comm* c : g->comms) clc_comm_destroy(c);
   delete g;
   return CLC_OK;

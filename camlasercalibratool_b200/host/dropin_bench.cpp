@@ -183,7 +183,7 @@ int main(int argc, char** argv) {
   // LM solve + report + analysis tail + tear-down) -- the headline.  call_*: the whole call expression on the caller's clock,
   // which adds what the by-value `obs` parameter costs the caller (move or deep copy before entry, destruction after return).
   std::vector<double> body, call_moved, call_lvalue, body_lvalue;
-  double phase_sum[7] = {0, 0, 0, 0, 0, 0, 0};
+  std::vector<double> phase[7];
   double max_dev = 0.0;
   for (int it = 0; it < warmup + steps; ++it) {
     Eigen::Matrix4d Tcl = Eigen::Matrix4d::Identity();
@@ -200,7 +200,7 @@ int main(int argc, char** argv) {
     if (it >= warmup) {
       call_moved.push_back(t1 - t0);
       body.push_back(ph[6]);
-      for (int k = 0; k < 7; ++k) phase_sum[k] += ph[k];
+      for (int k = 0; k < 7; ++k) phase[k].push_back(ph[k]);
     }
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 4; ++c) max_dev = std::max(max_dev, std::fabs(Tcl(r, c) - ref_T[r * 4 + c]));
@@ -222,12 +222,13 @@ int main(int argc, char** argv) {
   double sum = 0.0;
   for (double v : body) sum += v;
   const double mean_body = sum / (double)body.size();
-  for (int k = 0; k < 7; ++k) phase_sum[k] /= (double)body.size();
+  double phase_sum[7];  // per-phase medians over the timed calls
+  for (int k = 0; k < 7; ++k) phase_sum[k] = median(phase[k]);
   const int sweeps_per_call = lm_sweeps + 1;  // + the un-robustified information sweep of the analysis tail (:318-362)
   std::printf(
       "CLC_DROPIN_JSON {\"frames\": %lld, \"beams\": %lld, \"points\": %lld, \"edges\": %d, \"n_devices\": %d, \"steps\": %d, \"warmup\": %d, "
       "\"body_ms_mean\": %.6f, \"body_ms_median\": %.6f, \"body_ms_min\": %.6f, \"body_ms_max\": %.6f, "
-      "\"phases_ms\": {\"marshal\": %.4f, \"upload\": %.4f, \"solve\": %.4f, \"report\": %.4f, \"information\": %.4f, \"destroy\": %.4f}, "
+      "\"phases_ms_median\": {\"marshal\": %.4f, \"upload\": %.4f, \"solve\": %.4f, \"report\": %.4f, \"information\": %.4f, \"destroy\": %.4f}, "
       "\"call_expr_moved_ms_median\": %.6f, \"call_expr_lvalue_ms_median\": %.6f, \"body_ms_in_lvalue_calls_median\": %.6f, "
       "\"caller_copy_of_obs_ms\": %.6f, \"caller_destruction_of_obs_ms\": %.6f, "
       "\"sweeps_per_call\": %d, \"lm_iterations\": %d, \"termination\": %d, "
