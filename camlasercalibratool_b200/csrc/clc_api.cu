@@ -2017,6 +2017,16 @@ int clc_debug_sweep_timing(clc_problem* p, const double pose7[7], int with_lm, i
   return CLC_OK;
 }
 
+// experiment builds (-DCLC_LM_PROFILE): clock stamps of the last on-device lm_update (see clc_lm.cuh); zeros otherwise
+int clc_debug_lm_profile(long long out[16]) {
+  if (!out) return fail(CLC_ERR_INVALID, "NULL argument");
+  for (int i = 0; i < 16; ++i) out[i] = 0;
+#ifdef CLC_LM_PROFILE
+  CLC_CUDA(cudaMemcpyFromSymbol(out, clc::g_lm_profile, sizeof(long long) * 16));
+#endif
+  return CLC_OK;
+}
+
 int clc_bench_h2d(int64_t bytes, int device, int reps, float* ms_each) {
   if (bytes < 1 || reps < 1 || !ms_each) return fail(CLC_ERR_INVALID, "bad h2d bench arguments");
   if (device >= 0) CLC_CUDA(cudaSetDevice(device));

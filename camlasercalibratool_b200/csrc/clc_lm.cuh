@@ -50,6 +50,17 @@ struct LmState {
   clc_lm_iteration trace[kTraceMax];
 };
 
+// -DCLC_LM_PROFILE: clock stamps at the section boundaries of the last lm_update that ran on the device (experiment builds only;
+// read back with clc_debug_lm_profile)
+#if defined(CLC_LM_PROFILE) && defined(__CUDACC__)
+__device__ long long g_lm_profile[16];
+#endif
+#if defined(CLC_LM_PROFILE) && defined(__CUDA_ARCH__)
+#define CLC_LM_STAMP(i) g_lm_profile[i] = clock64()
+#else
+#define CLC_LM_STAMP(i) ((void)0)
+#endif
+
 CLC_HD double norm7(const double* a) {
   double s = 0.0;
   for (int i = 0; i < 7; ++i) s += a[i] * a[i];
@@ -90,6 +101,7 @@ CLC_HD void lm_init(LmCore* s, const double* pose7, const clc_lm_options& opt) {
 // terminates (s->done != 0) or has a new candidate in s->cand for the next sweep.
 CLC_HD void lm_update(LmCore* s, clc_lm_iteration* trace, const double* sums) {
   if (s->done) return;
+  CLC_LM_STAMP(0);
   s->sweeps++;
   const clc_lm_options& o = s->opt;
   clc_lm_iteration last;
@@ -156,6 +168,7 @@ CLC_HD void lm_update(LmCore* s, clc_lm_iteration* trace, const double* sums) {
     }
   }
 
+  CLC_LM_STAMP(1);  // accept / reject decided (incl. gradient_max_norm of an accepted step)
   for (;;) {
     // ---- Ceres: FinalizeIterationAndCheckIfMinimizerCanContinue ----
     if (last.step_is_successful) s->num_successful++; else s->num_unsuccessful++;
@@ -169,6 +182,7 @@ CLC_HD void lm_update(LmCore* s, clc_lm_iteration* trace, const double* sums) {
     }
     if (!(s->radius > o.min_trust_region_radius)) { s->done = CLC_TERM_CONVERGENCE_MIN_RADIUS; return; }
 
+    CLC_LM_STAMP(2);  // iteration recorded, termination tests done
     // ---- Ceres: LevenbergMarquardtStrategy::ComputeStep on the Jacobi-scaled system ----
     double Hs[36], gs[6], A[36], step[6];
 #pragma unroll
@@ -194,7 +208,9 @@ CLC_HD void lm_update(LmCore* s, clc_lm_iteration* trace, const double* sums) {
     const double inv_radius = 1.0 / s->radius;
 #pragma unroll
     for (int k = 0; k < 6; ++k) A[k * 6 + k] += s->diag[k] * inv_radius;  // D^2 = diag / radius
+    CLC_LM_STAMP(3);  // scaled, damped system built
     bool ok = chol6_solve(A, gs, step);
+    CLC_LM_STAMP(4);  // Cholesky solve done
     s->reuse_diagonal = 1;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -230,9 +246,11 @@ CLC_HD void lm_update(LmCore* s, clc_lm_iteration* trace, const double* sums) {
     s->num_invalid = 0;
     double delta[6];
     for (int k = 0; k < 6; ++k) delta[k] = step[k] * s->scale[k];
+    CLC_LM_STAMP(5);  // model cost change done
     pose_plus(s->x, delta, s->cand);
     s->model_cost_change = mcc;
     s->phase = 1;
+    CLC_LM_STAMP(6);  // candidate pose done
     return;
   }
 }

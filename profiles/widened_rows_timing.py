@@ -42,6 +42,27 @@ out["line_fit"] = {"scans": n_scans, "points_per_scan": n_pts, "gpu_ms_batch": m
                    "lm_sweeps_total": sweeps, "streamed_GBps": sweeps * n_pts * 16 / (ms * 1e-3) / 1e9,
                    "cpu_oracle_ms_per_scan_1_thread": cpu_ms, "cpu_scans_per_s": 1e3 / cpu_ms}
 
+# ---- rank 1, per call: LineFittingCeres(Points, Line) on ONE scan, as reference main/calibr_offline.cpp:124 calls it ------------
+from camlasercalibratool_b200 import LineFittingCeres  # noqa: E402
+
+per_call = {}
+for npts in (200, 1000):
+    scan = np.ascontiguousarray(d["points"][:npts])
+    for _ in range(20):
+        LineFittingCeres(scan, np.zeros(2))
+    ts = []
+    for _ in range(200):
+        line = np.zeros(2)
+        t0 = time.perf_counter()
+        LineFittingCeres(scan, line)
+        ts.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    for _ in range(100):
+        O.line_fit(scan)
+    per_call[str(npts)] = {"gpu_ms_per_call_median": 1e3 * float(np.median(ts)), "gpu_ms_per_call_min": 1e3 * float(np.min(ts)),
+                           "cpu_oracle_ms_per_call": 1e3 * (time.perf_counter() - t0) / 100}
+out["line_fit_per_call"] = per_call
+
 # ---- rank 4: TranScanToPoints + AutoGetLinePts, batched: 10^4 scans x 1081 beams from host memory ----------------------
 rng = np.random.default_rng(0)
 n_beams = 1081
