@@ -512,6 +512,8 @@ def run_ours(args):
             big.set_planar_mode(1)
             r3p = kernel_row(big, x, 20, peaks, "planar, 16 B/residual")
             _, r3p["full_lm_solve"] = solve_row(big, opt, 2, 2e8, max_over_ranks, barrier)
+            r3["traffic"] = (traffic.get("config3") or {}).get("dram_bytes_per_launch")
+            r3p["traffic"] = ((traffic.get("config3") or {}).get("planar") or {}).get("dram_bytes_per_launch")
             r3["planar"] = r3p
             r3["workload"] = "BASELINE configs[2]: 100000 frames x 2000 points (4.8 GB)"
             roofline["config3"] = r3
@@ -523,6 +525,7 @@ def run_ours(args):
             r5["gt_rot_err_rad"], r5["gt_trans_err_m"] = pose_error_vs_ground_truth(x5)
             c5.set_planar_mode(1)
             r5p = kernel_row(c5, x, 20, peaks, "planar + edge tail, 16 B/residual + 56 B/edge residual")
+            r5["traffic"] = (traffic.get("config5") or {}).get("dram_bytes_per_launch")
             r5["planar"] = r5p
             r5["workload"] = ("BASELINE configs[4]: 100000 frames x 2000 points + 200000 board-edge residuals, board poses from "
                               "the equidistant (Kannala-Brandt) camera chain with 0.3 px corner noise")

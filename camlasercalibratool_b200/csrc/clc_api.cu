@@ -377,11 +377,26 @@ int allreduce_sums(clc_problem* p, int count) {
   return CLC_OK;
 }
 
+// Waits for a stream with a short spin before blocking: a blocking cudaStreamSynchronize puts the thread to sleep and the wake-up
+// costs tens of microseconds (measured: 40-90 us per mid-solve poll inside a CPU-quota'd container, profiles/r2_loop_modes2.txt),
+// which is as long as a whole sweep at BASELINE configs[1].  Work that takes longer than the spin budget falls back to blocking.
+cudaError_t sync_stream_low_latency(cudaStream_t st) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    const cudaError_t e = cudaStreamQuery(st);
+    if (e != cudaErrorNotReady) return e;
+    if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(400)) return cudaStreamSynchronize(st);
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+
 // a peer that never answered the in-kernel exchange (5 s time-out) is an error, not a hang
 int check_p2p_error(clc_problem* p) {
   int err = 0;
   CLC_CUDA(cudaMemcpyAsync(&err, p->p2p_error, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
-  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  CLC_CUDA(sync_stream_low_latency(p->stream));
   if (err == 2) return fail(CLC_ERR_CUDA, "sweep kernel: the persistent grid was not co-resident (ticket wait timed out)");
   if (err) return fail(CLC_ERR_NCCL, "peer exchange timed out: a rank did not reach the collective");
   return CLC_OK;
@@ -975,7 +990,7 @@ static int eval_enqueue(clc_problem* p, const double pose7[7], bool loss, bool e
 static int eval_wait(clc_problem* p) {
   int rc = set_device(p);
   if (rc != CLC_OK) return rc;
-  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  CLC_CUDA(sync_stream_low_latency(p->stream));
   return check_p2p_error(p);
 }
 
@@ -1171,7 +1186,7 @@ int solve_finish(clc_problem* p, double pose7[7], clc_lm_summary* summary, clc_l
   if (rc != CLC_OK) return rc;
   CLC_CUDA(cudaEventRecord(p->ev1, p->stream));
   CLC_CUDA(cudaMemcpyAsync(p->h_lm, p->lm, sizeof(clc::LmState), cudaMemcpyDeviceToHost, p->stream));
-  CLC_CUDA(cudaStreamSynchronize(p->stream));
+  CLC_CUDA(sync_stream_low_latency(p->stream));
   float ms = 0.f;
   CLC_CUDA(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
   rc = check_p2p_error(p);
@@ -1224,7 +1239,10 @@ int solve_all(clc_problem* const* ps, int n, double pose7[7], const clc_lm_optio
     launched = max_sweeps;
   }
   while (launched < max_sweeps) {
-    const int batch = std::min(opt.iterations_per_sync, max_sweeps - launched);
+    // the first batch is twice as long: a solve from the identity or from the closed form takes 6-16 sweeps (reference sizes and
+    // BASELINE configs alike), and every host poll in the middle of a solve stalls the device for longer than the two or three
+    // no-op sweeps a too-long batch costs (3 us each; profiles/r2_loop_modes2.txt)
+    const int batch = std::min(launched == 0 ? 2 * opt.iterations_per_sync : opt.iterations_per_sync, max_sweeps - launched);
     // iteration-major order: sweep i of every shard is queued before sweep i+1 of any, so no device's queue can fill up
     // with kernels that wait for a peer whose launches have not been issued yet
     for (int i = 0; i < batch; ++i)
@@ -1241,7 +1259,7 @@ int solve_all(clc_problem* const* ps, int n, double pose7[7], const clc_lm_optio
     for (int g = 0; g < n; ++g) {
       rc = set_device(ps[g]);
       if (rc != CLC_OK) return rc;
-      CLC_CUDA(cudaStreamSynchronize(ps[g]->stream));
+      CLC_CUDA(sync_stream_low_latency(ps[g]->stream));
       all_done = all_done && (*ps[g]->h_done != 0);
     }
     if (all_done) break;

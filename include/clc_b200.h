@@ -109,7 +109,7 @@ typedef struct {
   double parameter_tolerance;       /* 1e-8 */
   int max_num_consecutive_invalid_steps; /* 5 */
   int jacobi_scaling;               /* 1 */
-  int iterations_per_sync;          /* LM iterations enqueued between host polls of the device `done` flag (8) */
+  int iterations_per_sync;          /* LM iterations enqueued between host polls of the device `done` flag (8; the first batch of a solve is twice as long) */
   int reserved;
 } clc_lm_options;
 

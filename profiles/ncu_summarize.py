@@ -8,8 +8,12 @@ KEYS = [
     ("gpu__time_duration.sum", "duration"),
     ("dram__bytes_read.sum", "dram read"),
     ("dram__bytes_write.sum", "dram write"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram throughput % of peak"),
-    ("lts__t_bytes.sum", "L2 bytes"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram throughput % of peak"),
+    ("dram__bytes.sum.per_second", "dram bytes/s"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput % of peak"),
+    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 pipe active %"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short scoreboard"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not selected"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
     ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 pipe %"),
@@ -54,5 +58,8 @@ for rec in out:
         if nice in rec and rec[nice] is not None:
             print(f"    {nice:32s} {rec[nice]:>18,.3f} {rec[nice + ' unit']}")
     if rec.get("dram read") is not None and rec.get("dram write") is not None:
-        print(f"    {'dram read + write':32s} {rec['dram read'] + rec['dram write']:>18,.3f} {rec['dram read unit']}")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = rec["dram read"] * scale[rec["dram read unit"]] + rec["dram write"] * scale[rec["dram write unit"]]
+        rec["dram bytes"] = tot
+        print(f"    {'dram read + write':32s} {tot:>18,.0f} byte")
 json.dump(out, open(sys.argv[1] + ".json", "w"), indent=1)
