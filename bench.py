@@ -304,6 +304,11 @@ def run_ours(args):
     if args.gpus != world:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local_rank)
+    # clocks: 100 ms sampling period and nvidia-smi needs ~1 s to deliver its first line, the timed region lasts ~20 ms -- the
+    # sampler therefore runs from here (problem generation, communicator set-up, warm-up, timed solves, roofline legs)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -383,9 +388,6 @@ def run_ours(args):
     total_points = float(sum_over_ranks(float(n_points))[0])
 
     # ---- resident-data leg: K full solves ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()  # 100 ms period: started before the warm-up so that the (short) timed region is inside the sampled window
     for _ in range(args.warmup):
         prob.solve(X0, opt)
     launches0 = launch_count()

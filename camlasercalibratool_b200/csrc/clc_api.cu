@@ -257,6 +257,8 @@ struct clc_problem {
   int64_t flush_n = 0;
   unsigned long long* timing = nullptr;  // profiling hook (clc_debug_sweep_timing)
   bool use_pdl = true;                   // CLC_PDL=0 disables programmatic dependent launch in the LM loop
+  int64_t l2_persist_bytes = 0;          // persisting-L2 window over the coordinate arrays during LM solves (0 = off)
+  bool l2_window_set = false;
   int loop_in_kernel = 1;                // CLC_LOOP_IN_KERNEL: 0 one launch per LM iteration; 1 single-block problems run the whole
                                          // LM loop in one launch; 2 every problem does (persistent grid, block 0 hands out the poses)
   // pinned host mirrors (views into one pooled block)
@@ -484,6 +486,7 @@ int finish_create(clc_problem* p) {
   p->grid_full = p->num_sms * blocks_per_sm;
   if (const char* env = std::getenv("CLC_PDL")) p->use_pdl = std::atoi(env) != 0;
   if (const char* env = std::getenv("CLC_LOOP_IN_KERNEL")) p->loop_in_kernel = std::atoi(env);
+  if (const char* env = std::getenv("CLC_L2_PERSIST_MB")) p->l2_persist_bytes = (int64_t)std::atoll(env) << 20;
   CLC_CUDA(cudaMallocAsync(&p->sums, sizeof(double) * clc::kMaxOut, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->pose, sizeof(double) * 8, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->launch_seq, sizeof(unsigned int), p->stream));
@@ -687,6 +690,7 @@ int clc_problem_destroy(clc_problem* p) {
     cudaStreamSynchronize(p->stream);
     cudaStreamDestroy(p->stream);
   }
+  if (p->l2_persist_bytes > 0) cudaCtxResetPersistingL2Cache();  // hand the set-aside lines back
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   pinned_release(p->pinned);
@@ -1135,8 +1139,44 @@ struct SolveCtx {
   bool fused_update = true, loss = true, edges = false;
 };
 
+// L2 residency across LM iterations: every iteration re-reads the same coordinate arrays.  When they are not much larger than
+// the 126 MB L2, a persisting access-policy window over the x,y block keeps a hash-selected share of their lines (hitRatio =
+// set-aside / window) resident from one sweep to the next, so that share is not fetched from HBM again.  The set-aside is a
+// device-wide limit: it is raised on first use and left in place.  Only the solve loop runs under the window; the measurement
+// hook clc_bench_eval (L2 flushed between launches: the 24 B / 16 B roofline rows) does not.
+int l2_window(clc_problem* p, bool on) {
+  if (p->l2_persist_bytes <= 0 || !p->xy_block) return CLC_OK;
+  if (on == p->l2_window_set) return CLC_OK;
+  cudaStreamAttrValue attr;
+  std::memset(&attr, 0, sizeof(attr));
+  if (on) {
+    int max_persist = 0, max_window = 0;
+    CLC_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, p->device));
+    CLC_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, p->device));
+    const size_t set_aside = (size_t)std::min<int64_t>(p->l2_persist_bytes, max_persist);
+    if (set_aside == 0 || max_window <= 0) return CLC_OK;
+    size_t cur = 0;
+    CLC_CUDA(cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize));
+    if (cur < set_aside) CLC_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+    const size_t span = sizeof(double) * (size_t)(p->y - p->x) + sizeof(double) * (size_t)p->n_points;  // x .. end of y
+    const size_t window = std::min(span, (size_t)max_window);
+    attr.accessPolicyWindow.base_ptr = p->xy_block;
+    attr.accessPolicyWindow.num_bytes = window;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)window);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    attr.accessPolicyWindow.num_bytes = 0;  // disables the window for later launches on the stream
+  }
+  CLC_CUDA(cudaStreamSetAttribute(p->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  p->l2_window_set = on;
+  return CLC_OK;
+}
+
 int solve_begin(clc_problem* p, const double pose7[7], const clc_lm_options& opt, SolveCtx* ctx) {
   int rc = set_device(p);
+  if (rc != CLC_OK) return rc;
+  rc = l2_window(p, true);
   if (rc != CLC_OK) return rc;
   ctx->opt = opt;
   clc::lm_init(&p->h_lm->core, pose7, opt);
@@ -1185,6 +1225,8 @@ int solve_finish(clc_problem* p, double pose7[7], clc_lm_summary* summary, clc_l
   int rc = set_device(p);
   if (rc != CLC_OK) return rc;
   CLC_CUDA(cudaEventRecord(p->ev1, p->stream));
+  rc = l2_window(p, false);
+  if (rc != CLC_OK) return rc;
   CLC_CUDA(cudaMemcpyAsync(p->h_lm, p->lm, sizeof(clc::LmState), cudaMemcpyDeviceToHost, p->stream));
   CLC_CUDA(sync_stream_low_latency(p->stream));
   float ms = 0.f;

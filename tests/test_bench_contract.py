@@ -23,3 +23,35 @@ def test_reference_arm_prints_one_contract_line():
     assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1 and cb["sample"]
     # the metric is the one BASELINE.json names
     assert "residual" in d["metric"].lower() and "residual" in json.dumps(base).lower()
+
+
+def test_both_arms_print_the_same_config():
+    """The driver compares the two arms' `config`: both come from one function (the reference arm's bounded sample is described
+    in its cpu_baseline.sample, not in config)."""
+    sys.path.insert(0, ROOT)
+    import argparse
+
+    import bench
+
+    a = argparse.Namespace(frames=10_000, beams=1_000)
+    c = bench.workload_config(a, 1)
+    assert set(c) == {"workload"} and "10000 frames x 1000 points" in c["workload"]
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count("workload_config(args, world)") == 3  # the definition + run_reference + run_ours
+
+
+def test_ground_truth_pose_error_is_accurate_near_zero():
+    """bench.py's check block measures the distance to the generator's ground truth: it must resolve 1e-12 rad (an arccos of
+    the trace would stop at 1e-8)."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+
+    import bench
+    from oracle import oracle as O
+
+    gt = O.ground_truth()[1]
+    ang, dt = bench.pose_error_vs_ground_truth(gt)
+    assert ang < 1e-15 and dt < 1e-15
+    x = O.pose_plus(gt, np.array([0, 0, 1e-9, 2e-12, 0, 0]))
+    ang, dt = bench.pose_error_vs_ground_truth(x)
+    assert abs(ang - 2e-12) < 1e-14 and abs(dt - 1e-9) < 1e-14

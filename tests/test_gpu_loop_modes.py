@@ -89,3 +89,20 @@ def test_per_scan_line_fit_equals_the_batched_kernel(oracle):
     line = np.array([0.3, -0.2])
     LineFittingCeres(np.zeros((0, 3)), line)  # an empty scan leaves a finite line (the reference would not even get here)
     assert np.all(np.isfinite(line))
+
+
+def test_l2_persistence_window_changes_no_bit(oracle, monkeypatch):
+    """CLC_L2_PERSIST_MB keeps a share of the coordinate arrays resident in L2 across the LM iterations of a solve: a cache
+    policy, not arithmetic -- the trajectory must be identical, and evaluations outside a solve are untouched."""
+    from camlasercalibratool_b200 import Problem
+
+    monkeypatch.setenv("CLC_PLANAR_MIN_POINTS", "0")
+    out = []
+    for mb in ("0", "32"):
+        monkeypatch.setenv("CLC_L2_PERSIST_MB", mb)
+        with Problem.synthetic(400, 700, seed=5, sigma=0.01) as g:
+            x, s, tr = g.solve(X0)
+            x2, s2, tr2 = g.solve(X0)
+            assert np.array_equal(x, x2)
+            out.append((x, [t.cost for t in tr], g.eval(x)[0], s.num_sweeps))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1] and out[0][2] == out[1][2] and out[0][3] == out[1][3]
