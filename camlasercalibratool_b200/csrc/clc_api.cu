@@ -20,6 +20,7 @@
 #include "../../include/clc_b200.h"
 #include "clc_kernels.cuh"
 #include "clc_linefit.cuh"
+#include "clc_small.cuh"
 
 namespace {
 
@@ -259,6 +260,7 @@ struct clc_problem {
   bool use_pdl = true;                   // CLC_PDL=0 disables programmatic dependent launch in the LM loop
   int64_t l2_persist_bytes = 0;          // persisting-L2 window over the coordinate arrays during LM solves (0 = off)
   bool l2_window_set = false;
+  bool small_kernel = true;              // CLC_SMALL_KERNEL=0: never use the one-cluster kernel of clc_small.cuh
   int loop_in_kernel = 1;                // CLC_LOOP_IN_KERNEL: 0 one launch per LM iteration; 1 single-block problems run the whole
                                          // LM loop in one launch; 2 every problem does (persistent grid, block 0 hands out the poses)
   // pinned host mirrors (views into one pooled block)
@@ -486,6 +488,7 @@ int finish_create(clc_problem* p) {
   p->grid_full = p->num_sms * blocks_per_sm;
   if (const char* env = std::getenv("CLC_PDL")) p->use_pdl = std::atoi(env) != 0;
   if (const char* env = std::getenv("CLC_LOOP_IN_KERNEL")) p->loop_in_kernel = std::atoi(env);
+  if (const char* env = std::getenv("CLC_SMALL_KERNEL")) p->small_kernel = std::atoi(env) != 0;
   if (const char* env = std::getenv("CLC_L2_PERSIST_MB")) p->l2_persist_bytes = (int64_t)std::atoll(env) << 20;
   CLC_CUDA(cudaMallocAsync(&p->sums, sizeof(double) * clc::kMaxOut, p->stream));
   CLC_CUDA(cudaMallocAsync(&p->pose, sizeof(double) * 8, p->stream));
@@ -1268,7 +1271,22 @@ int solve_all(clc_problem* const* ps, int n, double pose7[7], const clc_lm_optio
   if (rc != CLC_OK) return rc;
   const int max_sweeps = ctx[0].max_sweeps;
   int launched = 0;
-  bool loop_launch = true;
+  // Small problems (the reference's own sizes): the whole solve in one launch of one thread-block cluster that keeps every
+  // residual in registers (clc_small.cuh) -- no TMA rings, no gather, no global round trip between two LM iterations.
+  if (n == 1 && ps[0]->small_kernel && ps[0]->loop_in_kernel >= 1 && ps[0]->nranks <= 1 && ctx[0].fused_update &&
+      ps[0]->n_points + (ctx[0].edges ? ps[0]->n_edges : 0) <= clc::kSmallMaxResiduals) {
+    clc_problem* p = ps[0];
+    rc = set_device(p);
+    if (rc != CLC_OK) return rc;
+    const clc::ProblemView v = make_view(p);
+    if (ctx[0].loss)
+      clc::clc_small_lm_kernel<true><<<clc::kSmallCluster, clc::kSmallThreads, 0, p->stream>>>(v, p->lm, max_sweeps, ctx[0].edges ? 1 : 0);
+    else
+      clc::clc_small_lm_kernel<false><<<clc::kSmallCluster, clc::kSmallThreads, 0, p->stream>>>(v, p->lm, max_sweeps, ctx[0].edges ? 1 : 0);
+    CLC_LAUNCH_CHECK();
+    launched = max_sweeps;
+  }
+  bool loop_launch = launched == 0;
   for (int g = 0; g < n; ++g)
     loop_launch = loop_launch && ctx[g].fused_update &&
                   (ps[g]->loop_in_kernel >= 2 || (ps[g]->loop_in_kernel == 1 && ps[g]->grid == 1 && ps[g]->nranks <= 1));

@@ -233,7 +233,9 @@ int upload_points(std::vector<UploadShard>& shards) {
     }
   }
   const int n_chunks = (int)chunks.size();
-  const int K = std::min(n_chunks, 2 + 2 * G);  // pinned slots in the ring
+  int K = 2 + 2 * G;  // pinned slots in the ring
+  if (const char* env = std::getenv("CLC_UPLOAD_SLOTS")) K = std::max(2, std::atoi(env));
+  K = std::min(n_chunks, K);
   PackPool* pool = direct ? nullptr : &PackPool::instance();
   const int parts = direct ? 1 : pool->size();
   if (!direct) {
