@@ -215,6 +215,47 @@ int upload_points(std::vector<UploadShard>& shards) {
     if (std::atoi(env) == 0) direct = false;
   }
 
+  // ---- small uploads (the reference's own sizes: a few thousand points): no pack pool to wake, no extra stream, no events --
+  // one pack on the calling thread into a pinned slot, one copy and one layout kernel per shard on the problem's stream.
+  if (!direct && total_points <= std::min<int64_t>(65536, chunk_points) && !std::getenv("CLC_UPLOAD_NO_FAST_PATH")) {
+    int rc = g_slots.ensure(1, sizeof(double) * 3 * (size_t)chunk_points);
+    if (rc != CLC_OK) return rc;
+    double* slot = static_cast<double*>(g_slots.slots[0]);
+    int64_t bytes_h2d = 0;
+    for (auto& s : shards) {
+      clc_problem* p = s.p;
+      const int64_t n = p->n_points;
+      if (n == 0) { p->host_planarity_known = true; p->z_all_zero = true; continue; }
+      CLC_CUDA(cudaSetDevice(p->device));
+      const bool nonplanar = pack_xy(s, 0, n, slot);
+      if (nonplanar) pack_xyz(s, 0, n, slot);
+      const size_t bytes = sizeof(double) * (nonplanar ? 3 : 2) * (size_t)n;
+      void* stage = nullptr;
+      CLC_CUDA(cudaMallocAsync(&stage, bytes, p->stream));
+      CLC_CUDA(cudaMemcpyAsync(stage, slot, bytes, cudaMemcpyHostToDevice, p->stream));
+      const unsigned blocks = (unsigned)((n + 255) / 256);
+      if (nonplanar) {
+        int rc2 = materialise_z(p);
+        if (rc2 != CLC_OK) return rc2;
+        clc::clc_aos_to_soa_kernel<<<blocks, 256, 0, p->stream>>>(static_cast<const double*>(stage), n, p->x, p->y, p->z, 0, p->d_nonplanar);
+      } else {
+        clc::clc_aos2_to_soa_kernel<<<blocks, 256, 0, p->stream>>>(static_cast<const double2*>(stage), n, p->x, p->y, p->z, 0);
+      }
+      g_launches.fetch_add(1);
+      CLC_CUDA(cudaGetLastError());
+      CLC_CUDA(cudaFreeAsync(stage, p->stream));
+      CLC_CUDA(cudaStreamSynchronize(p->stream));  // the pinned slot is free again (the next shard / upload packs into it)
+      p->host_planarity_known = true;
+      p->z_all_zero = !nonplanar;
+      bytes_h2d += (int64_t)bytes;
+    }
+    g_last_upload.bytes_h2d = bytes_h2d;
+    g_last_upload.chunks = (int)shards.size();
+    g_last_upload.threads = 1;
+    g_last_upload.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return CLC_OK;
+  }
+
   struct Chunk { int shard; int64_t a, b; };
   std::vector<Chunk> chunks;
   {

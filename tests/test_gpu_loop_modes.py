@@ -158,7 +158,8 @@ def test_one_cluster_kernel_follows_the_oracle(oracle, monkeypatch, case):
             ang, dt = oracle.pose_error(x, xo)
             assert ang < 1e-6 and dt < 1e-6, (case, ang, dt)
             assert s.termination == so.termination and s.num_iterations == so.num_iterations, (case, s.termination, so.termination)
-            np.testing.assert_allclose([t.cost for t in tr], [t.cost for t in tro][: len(tr)], rtol=1e-9)
+            # (absolute floor: on noise-free data the cost falls to ~1e-20, where the summation order decides the digits)
+            np.testing.assert_allclose([t.cost for t in tr], [t.cost for t in tro][: len(tr)], rtol=1e-9, atol=1e-14 * tro[0].cost)
             x2, s2, _ = g.solve(x0)
             assert np.array_equal(x, x2)  # bit-reproducible
 
