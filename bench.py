@@ -6,16 +6,21 @@ simulation generator (main/calibr_simulation.cpp:10-108, exact-M mode, 1 cm rang
 A "step" is one complete CamLaserCalibration-equivalent solve: the on-device Levenberg-Marquardt loop to Ceres'
 convergence criteria, one fused residual+Jacobian+reduce sweep over every point per LM iteration.
 
-  value     residual+Jacobian evaluations / s over the whole job, data already resident in HBM
-  e2e       the same through the public API with HOST (pinned) buffers: H2D upload + HBM layout + solve + D2H result
-  roofline  the fused sweep kernel alone: algorithmic bytes (24 B/residual + 40 B/frame + 224 B) / CUDA-event time
-            per launch, L2 flushed between launches, against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline / --impl reference   the CPU oracle port of the reference algorithm (Ceres-shaped: materialised
-            Jacobian + dense QR, evaluation threaded over all host cores) on a bounded sample of the same workload.
+One JSON line; everything the driver's parser keeps is nested under the contract keys:
+  value     residual+Jacobian evaluations / s over the whole job, data already resident in HBM (CUDA-event time, max over ranks)
+  e2e       the same through the reference's OWN C++ call: host/dropin_bench.cpp builds a std::vector<Oberserve> (one pageable
+            heap array per frame) and times CamLaserCalibration(obs, Tcl, false) of the drop-in, entry to return -- gather/pack,
+            PCIe, HBM layout, LM solve, analysis tail, tear-down; N ranks: rank 0 runs it on N devices of one process
+  roofline  the fused sweep kernel alone: algorithmic bytes (24 B/residual + 40 B/frame + 224 B) / CUDA-event time per launch,
+            L2 flushed between launches, against the measured HBM copy bandwidth (MEASURED_PEAKS.json); nested: .planar (16 B per
+            residual, own denominator), .config3 (10^5 x 2000, 4.8 GB), .config5 (+ board-edge residuals, camera-chain poses)
+  config    workload + .check (noise-free ground truth < 1e-9; collective evaluation = sum of the shards'), .strong_scaling
+            (BASELINE configs[3], 2*10^9 residuals split over the N ranks), .step_device_ms (min / median / max of the K solves)
+  cpu_baseline / --impl reference   the CPU oracle port of the reference algorithm (Ceres-shaped: materialised Jacobian + dense
+            QR, evaluation threaded over the host cores) on a bounded sample of the same workload.
 
-Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank holds 10^4 frames of a 10^4 x N frame problem;
-the 28 normal-equation sums are all-reduced (NCCL, 224 B) after every sweep and every rank runs the identical LM
-update on its device.
+Multi-GPU (torchrun, one rank per GPU): weak scaling -- every rank holds 10^4 frames of a 10^4 x N frame problem; the 28
+normal-equation sums are exchanged inside the sweep kernel (NVLink peer stores) and every rank runs the identical LM update.
 """
 from __future__ import annotations
 

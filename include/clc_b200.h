@@ -176,7 +176,10 @@ int clc_problem_download_true_poses(const clc_problem* p, double* frame_pose_tru
 int clc_eval(clc_problem* p, const double pose7[7], double H36[36], double g6[6], double* cost);
 
 /* replaces: ceres::Solve() at reference src/LaseCamCalCeres.cpp:306-307 with the options of :302-304.
- * pose7 is in/out.  trace may be NULL.  Collective over the communicator's ranks. */
+ * pose7 is in/out.  trace may be NULL.  Collective over the communicator's ranks.
+ * The whole Levenberg-Marquardt loop runs on the device: one K1 sweep per iteration, chained with programmatic dependent
+ * launch, the host only polls a `done` flag; problems of the reference's own size (<= 16384 residuals, single rank) are solved
+ * by ONE launch of the one-cluster kernel K2 (csrc/clc_small.cuh) that keeps the residuals in registers. */
 int clc_solve_lm(clc_problem* p, double pose7[7], const clc_lm_options* opt, clc_lm_summary* summary,
                  clc_lm_iteration* trace, int trace_cap);
 
