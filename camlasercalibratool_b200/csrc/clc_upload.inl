@@ -56,8 +56,18 @@ class PackPool {
     int n = 0;
     if (const char* env = std::getenv("CLC_PACK_THREADS")) n = std::atoi(env);
     if (n <= 0) {
+      // Measured (profiles/r2_dropin_*.txt): 8 threads already saturate what the host memory system gives this pipeline, 12 and
+      // 16 are no faster.  Stay below the CPUs the process may really use: a container often has a CFS quota far below the
+      // visible core count (cgroup v2 cpu.max), and a pool that oversubscribes it gets throttled for whole scheduler periods.
       const int hw = (int)std::thread::hardware_concurrency();
-      n = std::max(1, std::min(16, hw - 1));
+      int usable = hw;
+      if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        long long quota = 0, period = 0;
+        if (std::fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0)
+          usable = std::min(usable, (int)(quota / period));
+        std::fclose(f);
+      }
+      n = std::max(1, std::min(12, usable - 2));
     }
     n = std::min(n, 64);
     for (int i = 0; i < n; ++i) threads_.emplace_back([this, i] { loop(i); });
