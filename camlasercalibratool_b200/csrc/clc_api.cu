@@ -398,6 +398,8 @@ cudaError_t sync_stream_low_latency(cudaStream_t st) {
 
 // a peer that never answered the in-kernel exchange (5 s time-out) is an error, not a hang
 int check_p2p_error(clc_problem* p) {
+  // only a multi-block gather or a peer exchange can raise the flag: single-block / one-cluster problems skip the round trip
+  if (p->grid <= 1 && p->nranks <= 1) return CLC_OK;
   int err = 0;
   CLC_CUDA(cudaMemcpyAsync(&err, p->p2p_error, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
   CLC_CUDA(sync_stream_low_latency(p->stream));
@@ -986,8 +988,20 @@ static int eval_enqueue(clc_problem* p, const double pose7[7], bool loss, bool e
     for (int i = 0; i < 7; ++i) h_pose[i] = ident[i];
   }
   CLC_CUDA(cudaMemcpyAsync(p->pose, h_pose, sizeof(double) * 7, cudaMemcpyHostToDevice, p->stream));
-  rc = launch_sweep(p, mode, loss, edges, p->pose, nullptr, nullptr);
-  if (rc != CLC_OK) return rc;
+  const bool with_edges = edges && p->n_edges > 0;
+  if (mode == clc::kModeLM && p->small_kernel && p->nranks <= 1 &&
+      p->n_points + (with_edges ? p->n_edges : 0) <= clc::kSmallMaxResiduals) {
+    // a small problem: one evaluation by the one-cluster kernel (clc_small.cuh)
+    const clc::ProblemView v = make_view(p);
+    if (loss)
+      clc::clc_small_lm_kernel<true, true><<<clc::kSmallCluster, clc::kSmallThreads, 0, p->stream>>>(v, nullptr, 1, with_edges ? 1 : 0, p->pose, p->sums);
+    else
+      clc::clc_small_lm_kernel<false, true><<<clc::kSmallCluster, clc::kSmallThreads, 0, p->stream>>>(v, nullptr, 1, with_edges ? 1 : 0, p->pose, p->sums);
+    CLC_LAUNCH_CHECK();
+  } else {
+    rc = launch_sweep(p, mode, loss, edges, p->pose, nullptr, nullptr);
+    if (rc != CLC_OK) return rc;
+  }
   rc = allreduce_sums(p, count);
   if (rc != CLC_OK) return rc;
   CLC_CUDA(cudaMemcpyAsync(p->h_sums, p->sums, sizeof(double) * count, cudaMemcpyDeviceToHost, p->stream));
@@ -1280,9 +1294,9 @@ int solve_all(clc_problem* const* ps, int n, double pose7[7], const clc_lm_optio
     if (rc != CLC_OK) return rc;
     const clc::ProblemView v = make_view(p);
     if (ctx[0].loss)
-      clc::clc_small_lm_kernel<true><<<clc::kSmallCluster, clc::kSmallThreads, 0, p->stream>>>(v, p->lm, max_sweeps, ctx[0].edges ? 1 : 0);
+      clc::clc_small_lm_kernel<true><<<clc::kSmallCluster, clc::kSmallThreads, 0, p->stream>>>(v, p->lm, max_sweeps, ctx[0].edges ? 1 : 0, nullptr, nullptr);
     else
-      clc::clc_small_lm_kernel<false><<<clc::kSmallCluster, clc::kSmallThreads, 0, p->stream>>>(v, p->lm, max_sweeps, ctx[0].edges ? 1 : 0);
+      clc::clc_small_lm_kernel<false><<<clc::kSmallCluster, clc::kSmallThreads, 0, p->stream>>>(v, p->lm, max_sweeps, ctx[0].edges ? 1 : 0, nullptr, nullptr);
     CLC_LAUNCH_CHECK();
     launched = max_sweeps;
   }

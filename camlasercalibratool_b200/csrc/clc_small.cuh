@@ -29,9 +29,11 @@ constexpr int kSmallCluster = 8;
 constexpr int kSmallItems = 8;  // residuals per thread
 constexpr int64_t kSmallMaxResiduals = (int64_t)kSmallThreads * kSmallCluster * kSmallItems;  // 16384
 
-template <bool LOSS>
+// EVAL: one evaluation at `eval_pose` instead of the LM loop -- the 28 sums go to `eval_sums` (clc_eval / clc_information of a
+// small problem: the same residual code, no LM state touched).
+template <bool LOSS, bool EVAL = false>
 __global__ void __cluster_dims__(kSmallCluster, 1, 1) __launch_bounds__(kSmallThreads, 1)
-clc_small_lm_kernel(ProblemView pv, LmState* lm, int max_sweeps, int use_edges) {
+clc_small_lm_kernel(ProblemView pv, LmState* lm, int max_sweeps, int use_edges, const double* eval_pose, double* eval_sums) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int rank = cluster.block_rank();
   __shared__ double s_w[kSmallThreads / 32][32];  // per-warp totals of the 28 sums
@@ -84,8 +86,8 @@ clc_small_lm_kernel(ProblemView pv, LmState* lm, int max_sweeps, int use_edges) 
 
   double pose[7];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) pose[i] = __ldcg(lm->core.cand + i);
-  if (rank == 0) {
+  for (int i = 0; i < 7; ++i) pose[i] = EVAL ? __ldcg(eval_pose + i) : __ldcg(lm->core.cand + i);
+  if (!EVAL && rank == 0) {
     const unsigned long long* g_core = reinterpret_cast<const unsigned long long*>(&lm->core);
     for (int k = tid; k < kLmCoreWords; k += kSmallThreads) s_core[k] = __ldcg(g_core + k);
   }
@@ -150,8 +152,9 @@ clc_small_lm_kernel(ProblemView pv, LmState* lm, int max_sweeps, int use_edges) 
         for (unsigned int r = 0; r < (unsigned int)kSmallCluster; ++r) t += *cluster.map_shared_rank(&s_blk[tid], r);
         s_tot[tid] = t;
       }
+      if (EVAL && tid < kNumSums) eval_sums[tid] = s_tot[tid];
       __syncthreads();
-      if (tid == 0) {
+      if (!EVAL && tid == 0) {
         double sums[kNumSums];
         for (int k = 0; k < kNumSums; ++k) sums[k] = s_tot[k];
         LmCore* core = reinterpret_cast<LmCore*>(s_core);
@@ -161,12 +164,13 @@ clc_small_lm_kernel(ProblemView pv, LmState* lm, int max_sweeps, int use_edges) 
       }
     }
     cluster.sync();  // the next pose is in CTA 0's shared memory (and CTA 0 is done reading the other CTAs' totals)
+    if (EVAL) break;
     const double* next = cluster.map_shared_rank(&s_pose[0], 0);
 #pragma unroll
     for (int i = 0; i < 7; ++i) pose[i] = next[i];
     if (next[7] != 0.0) break;
   }
-  if (rank == 0) {
+  if (!EVAL && rank == 0) {
     __syncthreads();
     unsigned long long* o_core = reinterpret_cast<unsigned long long*>(&lm->core);
     for (int k = tid; k < kLmCoreWords; k += kSmallThreads) o_core[k] = s_core[k];

@@ -10,12 +10,15 @@ from conftest import pack_sums
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["planar-auto", "general"])
+@pytest.fixture(autouse=True, params=["planar-auto", "general", "one-cluster"])
 def sweep_kernel_family(request, monkeypatch):
     """The generator's laser is two-dimensional (z == 0), which the library detects and serves with its two-stream
-    kernels; every test of this module runs a second time with the general three-stream kernels forced."""
+    kernels; every test of this module runs a second time with the general three-stream kernels forced -- both with the
+    one-cluster kernel for small problems (csrc/clc_small.cuh) switched OFF, so that the streaming kernels meet the small
+    and odd shapes too -- and a third time with it ON (the default), where problems up to 16384 residuals take that path."""
     monkeypatch.setenv("CLC_PLANAR", "1" if request.param == "planar-auto" else "0")
     monkeypatch.setenv("CLC_PLANAR_MIN_POINTS", "0")  # also for the small problems, which would otherwise stay general
+    monkeypatch.setenv("CLC_SMALL_KERNEL", "1" if request.param == "one-cluster" else "0")
     return request.param
 
 X0 = np.array([0, 0, 0, 0, 0, 0, 1.0])
