@@ -456,6 +456,11 @@ def run_ours(args):
         _, srow = solve_row(prob, opt, args.steps, total_points, max_over_ranks, barrier)
         row["full_lm_solve"] = srow
         roofline["planar"] = row
+    # the sampler ran from process start over the warm-up, the timed solves and the roofline legs (nvidia-smi needs a second or
+    # two before its first line, the timed solves last 20 ms); it stops here: the 48 GB strong-scaling leg below runs into
+    # the software power cap and is not what `value` / `roofline` were measured under
+    clocks = sampler.stop() if rank == 0 else None
+
     # ---- strong scaling: BASELINE configs[3] (10^6 frames x 2*10^3 points = 2*10^9 residuals, 48 GB) over the N ranks ----
     strong = None
     if not args.no_strong:
@@ -542,8 +547,6 @@ def run_ours(args):
     if world > 1:
         dist.barrier(group=cpu_group)
 
-    # the sampler ran over the whole job (nvidia-smi needs a second or two before its first line; the timed solves last 20 ms)
-    clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         cfg = workload_config(args, world)
         cfg.update({"sharding": (f"frames by rank, {world} ranks, 28-double all-reduce per sweep: " +
