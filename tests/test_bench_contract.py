@@ -55,3 +55,11 @@ def test_ground_truth_pose_error_is_accurate_near_zero():
     x = O.pose_plus(gt, np.array([0, 0, 1e-9, 2e-12, 0, 0]))
     ang, dt = bench.pose_error_vs_ground_truth(x)
     assert abs(ang - 2e-12) < 1e-14 and abs(dt - 1e-9) < 1e-14
+
+
+def test_reference_arm_under_torchrun_only_rank0_works():
+    """`bench.py --impl reference` launched with N ranks: rank 0 alone runs and prints, the others exit 0 without work."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert res.returncode == 0 and res.stdout.strip() == ""
