@@ -67,7 +67,7 @@ class PackPool {
           usable = std::min(usable, (int)(quota / period));
         std::fclose(f);
       }
-      n = std::max(1, std::min(12, usable - 2));
+      n = std::max(1, std::min(16, usable - 1));  // an upload to ONE device uses at most 12 of them (upload_points)
     }
     n = std::min(n, 64);
     for (int i = 0; i < n; ++i) threads_.emplace_back([this, i] { loop(i); });
@@ -288,7 +288,9 @@ int upload_points(std::vector<UploadShard>& shards) {
   if (const char* env = std::getenv("CLC_UPLOAD_SLOTS")) K = std::max(2, std::atoi(env));
   K = std::min(n_chunks, K);
   PackPool* pool = direct ? nullptr : &PackPool::instance();
-  const int parts = direct ? 1 : pool->size();
+  // workers used by this upload: one device is saturated by ~8-12 packers (more only oversubscribe a CPU quota and produce
+  // outliers); several devices are fed in parallel and are host-bound, so they get the whole pool
+  const int parts = direct ? 1 : std::min(pool->size(), 8 + 4 * G);
   if (!direct) {
     int rc = g_slots.ensure(K, sizeof(double) * 3 * (size_t)chunk_points);
     if (rc != CLC_OK) return rc;
@@ -327,7 +329,8 @@ int upload_points(std::vector<UploadShard>& shards) {
     *b = ch.a + n * (q + 1) / parts;
   };
   if (!direct) {
-    pool->start([&](int) {
+    pool->start([&](int worker) {
+      if (worker >= parts) return;
       for (;;) {
         const int64_t j = next_job.fetch_add(1);
         if (j >= n_jobs) return;
