@@ -1811,6 +1811,7 @@ int resolve_devices(const int* devices, int n_devices, std::vector<int>* out) {
 int clc_group_destroy(clc_group* g) {
   if (!g) return CLC_OK;
   bool clean = true;  // a group whose exchange timed out must not hand its mailboxes to the next one
+  if (!g->comms.empty())
   for (clc_problem* p : g->problems) {
     int err = 0;
     if (p->p2p_error && cudaSetDevice(p->device) == cudaSuccess && cudaStreamSynchronize(p->stream) == cudaSuccess &&
