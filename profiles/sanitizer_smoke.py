@@ -12,6 +12,24 @@ from oracle import oracle as O  # noqa: E402
 
 x0 = np.array([0, 0, 0, 0, 0, 0, 1.0])
 os.environ.setdefault("CLC_PLANAR_MIN_POINTS", "0")  # the two-stream kernels also on these small problems
+# round 2: the loop drivers and the one-cluster kernel (cluster barriers, distributed shared memory) on a small problem
+from camlasercalibratool_b200 import LineFittingCeres  # noqa: E402
+
+ps = O.generate(50, 180, seed=1, sigma=0.01, with_edges=False)
+for small, loop in (("1", "1"), ("0", "1"), ("0", "0"), ("0", "2")):
+    os.environ["CLC_SMALL_KERNEL"], os.environ["CLC_LOOP_IN_KERNEL"] = small, loop
+    with Problem.from_arrays(ps.frame_pose, ps.offsets, ps.points) as g:
+        c, H, gr = g.eval(x0)
+        x, s, tr = g.solve(x0)
+        g.information(x)
+        xo, so, _ = O.solve(ps, x0)
+        assert O.pose_error(x, xo)[0] < 1e-8 and s.termination == so.termination, (small, loop)
+line = np.zeros(2)
+LineFittingCeres(ps.points[:150], line)  # the per-scan light path
+os.environ["CLC_SMALL_KERNEL"], os.environ["CLC_LOOP_IN_KERNEL"] = "0", "2"
+with Problem.synthetic(300, 700, seed=2, sigma=0.01) as g:  # persistent multi-block grid: tagged-word gather + pose hand-out
+    g.solve(x0)
+os.environ["CLC_SMALL_KERNEL"], os.environ["CLC_LOOP_IN_KERNEL"] = "0", "1"  # below: the streaming kernels on everything
 for planar in ("1", "0"):
     os.environ["CLC_PLANAR"] = planar
     for edges in (False, True):
