@@ -416,6 +416,12 @@ def run_ours(args):
     step_stats = {"min": float(np.min(per_step)), "median": float(np.median(per_step)), "max": float(np.max(per_step)),
                   "first": float(per_step[0]), "what": "device ms per solve on rank 0"}
 
+    # ---- clocks: the timed region lasts ~20 ms, nvidia-smi samples every 100 ms and needs a second or so before its first line:
+    #      keep the device in exactly the timed region's state (the same solves, untimed) for ~2 s so that the sampler sees it ----
+    for _ in range(2500):
+        prob.solve(X0, opt)
+    barrier()
+
     # ---- check block (outside every timed region): the answer, at this N ----
     check = {}
     cost_c, H_c, g_c = prob.eval(x)  # collective (fused exchange when world > 1)
