@@ -89,6 +89,41 @@ CLC_HD void expand_lm(const double* plane, const double* m, double c, double s2,
   out[27] += use_loss ? 0.5 * a2 * s2 * cost_term : 0.5 * s2 * cost_term;
 }
 
+// One residual added DIRECTLY to acc[28] (21 upper-tri H, 6 g, cost) -- what the one-cluster kernel for small problems does
+// (clc_small.cuh): no moments, the plain PointInPlaneFactor arithmetic of reference src/LaseCamCalCeres.cpp:43-66 with the
+// Cauchy correction of :249.  plane = (n, d); (x, y, z) the laser point; s2 = 1/#points of the frame (the squared scale of
+// :239-240); a2 = cauchy_a^2, inv_a2 = 1/a2.  J = s [n, p x m] with m = R^T n; w = rho' = 1/(1 + e^2/a^2).
+CLC_HD void accumulate_residual(const PoseConsts& pc, const double* plane, double x, double y, double z, double s2, bool use_loss,
+                                double a2, double inv_a2, double* acc) {
+  double m[3], c;
+  frame_consts(pc, plane, m, &c);
+  const double e = fma(m[0], x, fma(m[1], y, fma(m[2], z, c)));
+  double w = 1.0, cost;
+  if (use_loss) {
+    const double u = fma(e * inv_a2, e, 1.0);
+    w = 1.0 / u;
+    cost = 0.5 * a2 * s2 * log(u);
+  } else {
+    cost = 0.5 * s2 * e * e;
+  }
+  const double J[6] = {plane[0], plane[1], plane[2], y * m[2] - z * m[1], z * m[0] - x * m[2], x * m[1] - y * m[0]};
+  const double ws = w * s2;
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    const double wa = ws * J[a];
+#pragma unroll
+    for (int b = a; b < 6; ++b) {
+      acc[k] = fma(wa, J[b], acc[k]);
+      ++k;
+    }
+  }
+  const double we = ws * e;
+#pragma unroll
+  for (int a = 0; a < 6; ++a) acc[21 + a] = fma(we, J[a], acc[21 + a]);
+  acc[27] += cost;
+}
+
 // Closed-form initialisation (reference src/LaseCamCalCeres.cpp:144-161): row A_k = n (x) (x, y, 1), b_k = -d, so
 // A^T A = sum_frames M (x) n n^T with M = sum_j pbar pbar^T (unweighted moments, z ignored) and
 // A^T b = sum_frames -d (M e_3) (x) n.   out[54] = 45 upper-tri of the 9x9 (row-major) then 9 of A^T b.

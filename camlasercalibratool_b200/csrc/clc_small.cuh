@@ -103,37 +103,10 @@ clc_small_lm_kernel(ProblemView pv, LmState* lm, int max_sweeps, int use_edges, 
     for (int j = 0; j < kSmallItems; ++j) {
       if (pl[j] == kNone) continue;
       const double* plane = pl[j] >= 0 ? pv.plane + (int64_t)pl[j] * 4 : pv.edge_plane + (int64_t)(-pl[j] - 1) * 4;
-      double pln[4], m[3], c;
+      double pln[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) pln[k] = plane[k];
-      frame_consts(pc, pln, m, &c);
-      const double x = px[j], y = py[j], z = pz[j];
-      const double e = fma(m[0], x, fma(m[1], y, fma(m[2], z, c)));
-      double w = 1.0, cost;
-      if (LOSS) {
-        const double u = fma(e * pv.inv_a2, e, 1.0);
-        w = 1.0 / u;
-        cost = 0.5 * pv.a2 * s2[j] * log(u);
-      } else {
-        cost = 0.5 * s2[j] * e * e;
-      }
-      // J = s [n, p x m]; everything below carries s^2 = s2
-      const double J[6] = {pln[0], pln[1], pln[2], y * m[2] - z * m[1], z * m[0] - x * m[2], x * m[1] - y * m[0]};
-      const double ws = w * s2[j];
-      int k = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        const double wa = ws * J[a];
-#pragma unroll
-        for (int b = a; b < 6; ++b) {
-          acc[k] = fma(wa, J[b], acc[k]);
-          ++k;
-        }
-      }
-      const double we = ws * e;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) acc[21 + a] = fma(we, J[a], acc[21 + a]);
-      acc[27] += cost;
+      accumulate_residual(pc, pln, px[j], py[j], pz[j], s2[j], LOSS, pv.a2, pv.inv_a2, acc);
     }
     // ---- cluster reduction, fixed order ----
     warp_transpose_sum<32>(acc, lane);  // lane L: this warp's total of sum L

@@ -75,6 +75,7 @@ class Harness:
         L.harness_lm_trace.argtypes = [C.c_void_p, C.c_int, C.POINTER(LmIteration)]
         L.harness_expand_lm.argtypes = [dp, dp, C.c_double, dp, C.c_int, C.c_double, C.c_double, dp]
         L.harness_frame_consts.argtypes = [dp, dp, dp, dp]
+        L.harness_accumulate_residual.argtypes = [dp, dp, dp, C.c_double, C.c_int, C.c_double, dp]
         L.harness_expand_closed.argtypes = [dp, dp, dp]
         L.harness_frame_plane.argtypes = [dp, dp]
         L.harness_edge_planes.argtypes = [dp, dp, dp]

@@ -35,6 +35,13 @@ void harness_expand_lm(const double* plane, const double* pose7, double count, c
   clc::frame_consts(pc, plane, m, &c);
   clc::expand_lm(plane, m, c, 1.0 / count, S10, use_loss != 0, cost_term, a2, out28);
 }
+// one residual added directly to the 28 sums: the per-residual code of the one-cluster kernel (csrc/clc_small.cuh)
+void harness_accumulate_residual(const double* plane, const double* pose7, const double* xyz, double count, int use_loss,
+                                 double a2, double* acc28) {
+  clc::PoseConsts pc;
+  clc::make_pose_consts(pose7, &pc);
+  clc::accumulate_residual(pc, plane, xyz[0], xyz[1], xyz[2], 1.0 / count, use_loss != 0, a2, 1.0 / a2, acc28);
+}
 void harness_frame_consts(const double* plane, const double* pose7, double* m3, double* c) {
   clc::PoseConsts pc;
   clc::make_pose_consts(pose7, &pc);

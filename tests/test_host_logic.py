@@ -243,3 +243,36 @@ def test_state_machine_soak_on_random_problems(harness, oracle):
         assert ang < 1e-6 and dt < 1e-6
         seen.add(so.termination)
     assert len(seen) >= 3  # function / parameter / gradient tolerance (and sometimes the iteration limit) all occur
+
+
+@pytest.mark.parametrize("edges,use_loss", [(False, True), (True, True), (True, False)])
+def test_direct_residual_accumulation_of_the_one_cluster_kernel(harness, oracle, edges, use_loss):
+    """csrc/clc_small.cuh adds every residual directly to the 28 sums (accumulate_residual, compiled here for the host from
+    the same source): summed over all residuals -- points with their frame's plane and 1/#points, edge residuals with their
+    edge plane -- it must give the oracle's (cost, H, g)."""
+    p = oracle.generate(30, 48, seed=4, sigma=0.02, exact_m=True, with_edges=edges, use_loss=use_loss)
+    rng = np.random.default_rng(5)
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    a2 = p.cauchy_a ** 2
+    for pose in (X0, oracle.ground_truth()[1], np.concatenate([rng.normal(size=3) * 0.3, q])):
+        pose = np.ascontiguousarray(pose, dtype=np.float64)
+        acc = np.zeros(28)
+        for f in range(p.n_frames):
+            plane = np.ascontiguousarray(oracle.frame_plane(p.frame_pose[f]), dtype=np.float64)
+            b, e = int(p.offsets[f]), int(p.offsets[f + 1])
+            for i in range(b, e):
+                xyz = np.ascontiguousarray(p.points[i], dtype=np.float64)
+                harness.L.harness_accumulate_residual(harness.dp(plane), harness.dp(pose), harness.dp(xyz), float(e - b),
+                                                      int(use_loss), a2, harness.dp(acc))
+            if edges and e > b:
+                p1, p2 = oracle.edge_planes(p.frame_pose[f])
+                for plane_e, xyz in ((p1, p.edge_points[f, :3]), (p2, p.edge_points[f, 3:])):
+                    plane_e = np.ascontiguousarray(plane_e, dtype=np.float64)
+                    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+                    harness.L.harness_accumulate_residual(harness.dp(plane_e), harness.dp(pose), harness.dp(xyz), float(e - b),
+                                                          int(use_loss), a2, harness.dp(acc))
+        cost, H, g = oracle.evaluate_normal(p, pose)
+        ref = pack_sums(cost, H, g)
+        np.testing.assert_allclose(acc[:27], ref[:27], rtol=0, atol=2e-13 * np.abs(ref[:21]).max())
+        assert abs(acc[27] - ref[27]) <= 2e-13 * abs(ref[27])
